@@ -1,0 +1,321 @@
+"""fast5 raw-signal access for the read-batching driver (host side, I/O stays on the CPU).
+
+Mirrors `STRique_lib/fast5Index.py` of the reference: `fast5Index(index_file).get_raw(ID)`
+(fast5Index.py:45-56, 76-84, 220-233) with the same index-line format
+(`relative/path.fast5[/group]<TAB>READ_ID`, fast5Index.py:163-179) and the same lookup rule
+(split on `(.fast5|.tar)/`, fast5Index.py:224).
+
+The reference reads HDF5 through h5py.  h5py is used here too when it is importable; otherwise the
+small pure-Python HDF5 subset reader below decodes what ONT fast5 files actually contain:
+superblock v0/v1, v1 object headers (+ continuation blocks), old-style groups (symbol table:
+B-tree v1 / SNOD / local heap), compact new-style groups (link messages), chunked (B-tree v1),
+contiguous or compact datasets of fixed-point integers, deflate and shuffle filters.
+"""
+import os
+import re
+import struct
+import tarfile
+import tempfile
+import zlib
+
+import numpy as np
+
+try:  # pragma: no cover - depends on the environment
+    import h5py as _h5py
+except Exception:  # noqa: BLE001
+    _h5py = None
+
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class HDF5Error(RuntimeError):
+    pass
+
+
+class _MiniHDF5:
+    """Read-only subset HDF5 reader (see module docstring)."""
+
+    def __init__(self, path):
+        with open(path, 'rb') as fp:
+            self.buf = fp.read()
+        b = self.buf
+        base = 0
+        while b[base:base + 8] != b'\x89HDF\r\n\x1a\n':
+            base = 512 if base == 0 else base * 2
+            if base >= len(b):
+                raise HDF5Error('not an HDF5 file: ' + path)
+        ver = b[base + 8]
+        if ver not in (0, 1):
+            raise HDF5Error('unsupported HDF5 superblock version {}'.format(ver))
+        self.O, self.L = b[base + 13], b[base + 14]
+        if self.O != 8 or self.L != 8:
+            raise HDF5Error('only 8-byte offsets/lengths are supported')
+        p = base + 24 + (4 if ver == 1 else 0)
+        self.base = self._u(p, 8)
+        p += 32                       # base, free-space, EOF, driver-info addresses
+        # root symbol table entry: link name offset, object header address, cache type, reserved, scratch
+        self.root = self._u(p + 8, 8)
+
+    # -- primitives -----------------------------------------------------------------------------
+    def _u(self, p, n):
+        return int.from_bytes(self.buf[p:p + n], 'little')
+
+    def _messages(self, addr):
+        """Yield (type, flags, payload bytes) of a version-1 object header."""
+        b = self.buf
+        addr += self.base
+        if b[addr:addr + 4] == b'OHDR':
+            raise HDF5Error('version-2 object headers are not supported')
+        if b[addr] != 1:
+            raise HDF5Error('unsupported object header version {}'.format(b[addr]))
+        nmsg = self._u(addr + 2, 2)
+        size = self._u(addr + 8, 4)
+        blocks = [(addr + 16, size)]
+        seen = 0
+        while blocks and seen < nmsg:
+            p, remaining = blocks.pop(0)
+            end = p + remaining
+            while p + 8 <= end and seen < nmsg:
+                mtype, msize, mflags = self._u(p, 2), self._u(p + 2, 2), b[p + 4]
+                payload = b[p + 8:p + 8 + msize]
+                p += 8 + msize
+                seen += 1
+                if mtype == 0x10:   # continuation
+                    blocks.append((self._u(p - msize, 8) + self.base, self._u(p - msize + 8, 8)))
+                    continue
+                yield mtype, mflags, payload
+
+    # -- groups ---------------------------------------------------------------------------------
+    def _heap_string(self, heap_addr, off):
+        h = heap_addr + self.base
+        if self.buf[h:h + 4] != b'HEAP':
+            raise HDF5Error('bad local heap')
+        data = self._u(h + 24, 8) + self.base
+        e = self.buf.index(b'\0', data + off)
+        return self.buf[data + off:e].decode('utf-8')
+
+    def _walk_group_btree(self, node_addr, heap_addr, out):
+        n = node_addr + self.base
+        sig = self.buf[n:n + 4]
+        if sig == b'TREE':
+            level, used = self.buf[n + 5], self._u(n + 6, 2)
+            p = n + 24
+            for k in range(used):
+                child = self._u(p + 8 + k * 16, 8)   # key(8) child(8) key(8) ...
+                self._walk_group_btree(child, heap_addr, out)
+        elif sig == b'SNOD':
+            nsym = self._u(n + 6, 2)
+            p = n + 8
+            for k in range(nsym):
+                e = p + k * 40
+                out[self._heap_string(heap_addr, self._u(e, 8))] = self._u(e + 8, 8)
+        else:
+            raise HDF5Error('bad group B-tree node')
+
+    def links(self, addr):
+        """name -> object header address of every member of the group at `addr`."""
+        out = {}
+        for mtype, _, d in self._messages(addr):
+            if mtype == 0x11:     # symbol table message: B-tree v1 + local heap
+                self._walk_group_btree(self._u_b(d, 0, 8), self._u_b(d, 8, 8), out)
+            elif mtype == 0x06:   # link message
+                flags = d[1]
+                p = 2
+                ltype = 0
+                if flags & 0x08:
+                    ltype = d[p]; p += 1
+                if flags & 0x04:
+                    p += 8
+                if flags & 0x10:
+                    p += 1
+                nlen_size = 1 << (flags & 3)
+                nlen = int.from_bytes(d[p:p + nlen_size], 'little'); p += nlen_size
+                name = d[p:p + nlen].decode('utf-8'); p += nlen
+                if ltype == 0:
+                    out[name] = int.from_bytes(d[p:p + 8], 'little')
+            elif mtype == 0x02:
+                # link info: dense storage (fractal heap) when the heap address is defined
+                flags = d[1]
+                p = 2 + (8 if flags & 1 else 0)
+                if int.from_bytes(d[p:p + 8], 'little') != _UNDEF:
+                    raise HDF5Error('densely stored groups (fractal heap) are not supported without h5py')
+        return out
+
+    @staticmethod
+    def _u_b(d, p, n):
+        return int.from_bytes(d[p:p + n], 'little')
+
+    def resolve(self, path):
+        addr = self.root
+        for part in [x for x in path.split('/') if x]:
+            members = self.links(addr)
+            if part not in members:
+                raise KeyError(path)
+            addr = members[part]
+        return addr
+
+    def find_signal(self, raw_group_path):
+        """Depth-first search below `raw_group_path` for the first member whose path contains
+        'Signal' (the reference uses h5py `visit`, fast5Index.py:80)."""
+        def visit(addr):
+            for name in sorted(self.links(addr)):
+                child = self.links(addr)[name]
+                if 'Signal' in name:
+                    return child
+                try:
+                    found = visit(child)
+                except HDF5Error:
+                    found = None
+                if found is not None:
+                    return found
+            return None
+        return visit(self.resolve(raw_group_path))
+
+    # -- datasets -------------------------------------------------------------------------------
+    def read_dataset(self, addr):
+        shape = dtype = layout = None
+        filters = []
+        for mtype, _, d in self._messages(addr):
+            if mtype == 0x01:
+                ver, rank, flags = d[0], d[1], d[2]
+                p = 8 if ver == 1 else 4
+                shape = tuple(self._u_b(d, p + 8 * k, 8) for k in range(rank))
+            elif mtype == 0x03:
+                cls, bits0, size = d[0] & 0x0F, d[1], self._u_b(d, 4, 4)
+                if cls != 0:
+                    raise HDF5Error('only fixed-point datasets are supported (class {})'.format(cls))
+                dtype = np.dtype(('>' if bits0 & 1 else '<') + ('i' if bits0 & 8 else 'u') + str(size))
+            elif mtype == 0x08:
+                if d[0] != 3:
+                    raise HDF5Error('unsupported data layout version {}'.format(d[0]))
+                layout = d
+            elif mtype == 0x0B:
+                ver, nf = d[0], d[1]
+                p = 8 if ver == 1 else 2
+                for _ in range(nf):
+                    fid = self._u_b(d, p, 2)
+                    if ver == 1 or fid >= 256:
+                        nlen = self._u_b(d, p + 2, 2); p += 2
+                    else:
+                        nlen = 0
+                    ncd = self._u_b(d, p + 4, 2)
+                    p += 6
+                    p += (nlen + 7) // 8 * 8 if ver == 1 else nlen
+                    cd = [self._u_b(d, p + 4 * k, 4) for k in range(ncd)]
+                    p += 4 * ncd
+                    if ver == 1 and ncd % 2:
+                        p += 4
+                    filters.append((fid, cd))
+        if shape is None or dtype is None or layout is None:
+            raise HDF5Error('incomplete dataset header')
+        n = int(np.prod(shape)) if shape else 1
+        cls = layout[1]
+        if cls == 0:     # compact
+            size = self._u_b(layout, 2, 2)
+            return np.frombuffer(layout[4:4 + size], dtype=dtype, count=n).reshape(shape).copy()
+        if cls == 1:     # contiguous
+            a = self._u_b(layout, 2, 8)
+            if a == _UNDEF:
+                return np.zeros(shape, dtype)
+            a += self.base
+            return np.frombuffer(self.buf[a:a + n * dtype.itemsize], dtype=dtype, count=n).reshape(shape).copy()
+        if cls != 2:
+            raise HDF5Error('unknown layout class')
+        rank = layout[2]
+        btree = self._u_b(layout, 3, 8)
+        cdims = tuple(self._u_b(layout, 11 + 4 * k, 4) for k in range(rank))[:-1]
+        if len(shape) != 1 or len(cdims) != 1:
+            raise HDF5Error('only 1-D chunked datasets are supported')
+        out = np.zeros(shape, dtype)
+        if btree != _UNDEF:
+            self._read_chunks(btree, rank, cdims[0], dtype, filters, out)
+        return out
+
+    def _read_chunks(self, node_addr, rank, clen, dtype, filters, out):
+        n = node_addr + self.base
+        if self.buf[n:n + 4] != b'TREE':
+            raise HDF5Error('bad chunk B-tree node')
+        level, used = self.buf[n + 5], self._u(n + 6, 2)
+        keysize = 8 + 8 * rank
+        p = n + 24
+        for k in range(used):
+            kp = p + k * (keysize + 8)
+            csize, fmask = self._u(kp, 4), self._u(kp + 4, 4)
+            off0 = self._u(kp + 8, 8)
+            child = self._u(kp + keysize, 8)
+            if level > 0:
+                self._read_chunks(child, rank, clen, dtype, filters, out)
+                continue
+            raw = self.buf[child + self.base:child + self.base + csize]
+            for idx in range(len(filters) - 1, -1, -1):
+                fid, cd = filters[idx]
+                if fmask & (1 << idx):
+                    continue
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    es = cd[0] if cd else dtype.itemsize
+                    arr = np.frombuffer(raw, dtype=np.uint8)
+                    cnt = len(arr) // es
+                    raw = arr[:cnt * es].reshape(es, cnt).T.tobytes() + arr[cnt * es:].tobytes()
+                elif fid == 3:
+                    raw = raw[:-4]
+                else:
+                    raise HDF5Error('HDF5 filter {} (e.g. VBZ=32020) needs h5py plus its plugin'.format(fid))
+            vals = np.frombuffer(raw, dtype=dtype, count=min(clen, len(raw) // dtype.itemsize))
+            take = min(len(vals), out.shape[0] - off0)
+            if take > 0:
+                out[off0:off0 + take] = vals[:take]
+
+
+def read_raw_signal(f5_file, offset=''):
+    """Raw DAC samples of one read: first dataset below `<offset>/Raw` whose name contains
+    'Signal' (fast5Index.py:76-84)."""
+    raw_group = '/'.join([x for x in (offset, 'Raw') if x])
+    if _h5py is not None:  # pragma: no cover - depends on the environment
+        with _h5py.File(f5_file, 'r') as fp:
+            s = fp[raw_group].visit(lambda name: name if 'Signal' in name else None)
+            return fp[raw_group + '/' + s][()]
+    f = _MiniHDF5(f5_file)
+    addr = f.find_signal(raw_group)
+    if addr is None:
+        raise HDF5Error('no Signal dataset below ' + raw_group)
+    return f.read_dataset(addr)
+
+
+class fast5Index(object):
+    """Index-file backed raw-signal lookup (fast5Index.py:45-56, 220-233)."""
+
+    def __init__(self, index_file=None, tmp_prefix=None):
+        self.index_file = index_file
+        self.tmp_prefix = tmp_prefix
+        if index_file and not os.path.exists(index_file):
+            raise RuntimeError('[Error] Raw fast5 index file {} not found.'.format(index_file))
+        elif index_file:
+            with open(index_file, 'r') as fp:
+                self.index_dict = {rid: path for path, rid in
+                                   [line.split('\t') for line in fp.read().split('\n') if line]}
+            self.index_dir = os.path.dirname(index_file)
+        else:
+            self.index_dict = None
+
+    def _get_raw(self, f5_file, ID, offset=''):
+        try:
+            return read_raw_signal(f5_file, offset)
+        except Exception:  # noqa: BLE001 - same catch-all as the reference
+            raise RuntimeError('[ERROR] Could not retrieve {ID} from file {file}.'.format(ID=ID, file=f5_file))
+
+    def get_raw(self, ID):
+        assert self.index_dict
+        if ID not in self.index_dict:
+            raise RuntimeError('[Error] Read {ID} not found in {index}.'.format(ID=ID, index=self.index_file))
+        target = re.split(r'(\.fast5|\.tar)\/', self.index_dict[ID])
+        if len(target) == 1:                  # single read file
+            return self._get_raw(os.path.join(self.index_dir, target[0]), ID)
+        if target[1] == '.fast5':             # bulk fast5
+            return self._get_raw(os.path.join(self.index_dir, target[0] + '.fast5'), ID, offset=target[2])
+        with tempfile.TemporaryDirectory(prefix=self.tmp_prefix) as tmp, \
+                tarfile.open(os.path.join(self.index_dir, target[0] + '.tar')) as tar:
+            member = tar.getmember(target[2])
+            tar.extract(member, path=tmp)
+            return self._get_raw(os.path.join(tmp, member.name), ID)
