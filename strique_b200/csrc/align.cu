@@ -1,0 +1,459 @@
+// Alignment kernels (see align.cuh for the design summary).
+#include "align.cuh"
+
+namespace strique {
+
+namespace {
+
+// SeqAn TraceBitMap_ (seqan/align/dp_trace_segment.h / dp_profile.h:124-133)
+constexpr unsigned T_DIAG = 1, T_HOR = 2, T_VER = 4, T_HOPEN = 8, T_VOPEN = 16, T_MAXH = 32, T_MAXV = 64;
+
+__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ---------------------------------------------------------------------------------------------
+// Score table: lut[code][level] = max(off - (float)pow((double)|v_code - y_level|, 1.2), min)
+// (src/score_distance.h:117-122; the subtraction is fp32, pow is fp64, the cast rounds to fp32).
+// CUDA's fp64 pow is accurate to 2 ulp; an entry whose fp64 result lies within 16 fp64-ulps of
+// an fp32 rounding midpoint is reported in lut_fix so the host can re-evaluate it with libm and
+// patch it -- this keeps the table bit-identical to the reference's.
+// ---------------------------------------------------------------------------------------------
+__global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S, int n_tasks) {
+    const int t = blockIdx.y;
+    if (t >= n_tasks) return;
+    const int K = task_K[t], S = task_S[t];
+    const int f = b.task_flank[t], sg = b.task_sig[t];
+    const int nlev_in = b.flank_off[f + 1] - b.flank_off[f];
+    const int rows = nlev_in * b.samples;
+    const int nlev = rows / S;            // levels as seen by the kernel
+    const int row_len = 32 * K;
+    const float *vals = b.code_values + (size_t)sg * b.n_code_values;
+    const float *lev = b.flank_levels + b.flank_off[f];
+    float *lut = b.lut + (size_t)t * b.lut_task_stride;
+    const int total = b.n_code_values * row_len;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c = e / row_len, u = e - c * row_len;
+        float out = 0.f;
+        if (u < nlev) {
+            const float h = vals[c], v = lev[(u * S) / b.samples];
+            const float d = h > v ? h - v : v - h;
+            const double x = pow((double)d, 1.2);
+            const float fx = (float)x;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+            const long long low = (long long)(bits & 0x1FFFFFFFull) - 0x10000000ll;
+            if ((low < 0 ? -low : low) <= 16 && b.lut_fix != nullptr) {
+                unsigned long long k = atomicAdd(b.lut_fix, 1ull);
+                if (k < (unsigned long long)b.lut_fix_cap)
+                    b.lut_fix[1 + k] = ((unsigned long long)t << 40) | (unsigned long long)e;
+            }
+            const float s = b.p.dist_offset - fx;
+            out = s > b.p.dist_min ? s : b.p.dist_min;
+        }
+        lut[e] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One systolic sweep of a warp over signal columns (j0, j1] of one task.
+//   Sv/Hv      : this lane's R rows of the S and H matrices at column j0 on entry, j1 on exit
+//   diag_next  : S[j0][lane*R] (value above the strip in the previous column) on entry
+// TRACE = false: score scan; tracks the best last-row cell and writes checkpoints.
+// TRACE = true : additionally packs SeqAn's trace flags, 4 bits per cell, into `trace`.
+// ---------------------------------------------------------------------------------------------
+template <int K, int S, bool TRACE>
+struct Sweep {
+    static constexpr int R = K * S;
+    static constexpr int W = (R + 7) / 8;
+
+    __device__ __forceinline__ static void run(
+        const uint16_t *__restrict__ codes, const int N, const float *__restrict__ lut, const int j0, const int j1,
+        const int lane, const int nl, const strique_align_params &p, float (&Sv)[R], float (&Hv)[R],
+        float diag_next,
+        // scan
+        const int lastlane, const int kL, float &best, int &bestj, float *__restrict__ ckS,
+        float *__restrict__ ckH, const int ckpt_rows,
+        // trace
+        uint32_t *__restrict__ trace, const int capture_j, float &capS, float &capH, float &capV) {
+        const float INF = STRIQUE_SEQAN_INF;
+        const float geh = p.gap_extension_h, gev = p.gap_extension_v, goh = p.gap_open_h, gov = p.gap_open_v;
+        const int row_len = 32 * K;
+        float lutc[K], lutn[K];
+        float botS = 0.f, botV = INF;
+        const int last_step = (j1 - j0) + nl - 1;
+        // software pipeline: scores of the next column are fetched while this one is computed
+        {
+            const int c = codes[clampi(j0 + 1 - lane - 1, 0, N - 1)];
+            const float *row = lut + (size_t)c * row_len + lane * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
+        }
+        int code_nx = codes[clampi(j0 + 2 - lane - 1, 0, N - 1)];
+        for (int s = 1; s <= last_step; ++s) {
+            const int j = j0 + s - lane;
+            {
+                const float *row = lut + (size_t)code_nx * row_len + lane * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k);
+            }
+            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];   // code of column j + 2
+            float inS = __shfl_up_sync(0xffffffffu, botS, 1);
+            float inV = __shfl_up_sync(0xffffffffu, botV, 1);
+            if (lane == 0) { inS = 0.f; inV = INF; }   // DP row 0: free begin, S = 0, V = "infinity"
+            if (j > j0 && j <= j1 && lane < nl) {
+                float diag = diag_next;
+                diag_next = inS;
+                float cS = inS, cV = inV;
+                uint32_t tw[W];
+                if (TRACE) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) tw[w] = 0u;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float sc = lutc[r / S];
+                    const float pS = Sv[r], pH = Hv[r];
+                    const float inter = diag + sc;
+                    diag = pS;
+                    const float eh = pH + geh, oh = pS + goh;
+                    const float ev = cV + gev, ov = cS + gov;
+                    if (TRACE) {
+                        // exact restatement of the SeqAn cell (dp_formula_affine.h:64-128)
+                        const bool hopen = eh < oh;
+                        const float h = hopen ? oh : eh;
+                        const bool vopen = ev < ov;
+                        cV = vopen ? ov : ev;
+                        const bool maxh = cV < h;
+                        const float g = maxh ? h : cV;
+                        const bool gap = inter < g;
+                        cS = gap ? g : inter;
+                        Hv[r] = h;
+                        const uint32_t nib = (gap ? (maxh ? 2u : 1u) : 0u) | (hopen ? 4u : 0u) | (vopen ? 8u : 0u);
+                        tw[r / 8] |= nib << (4 * (r % 8));
+                        if ((r + 1) % S == 0 && j == capture_j && lane == lastlane && kL == r / S) {
+                            capS = cS; capH = h; capV = cV;
+                        }
+                    } else {
+                        const float h = fmaxf(eh, oh);
+                        cV = fmaxf(ev, ov);
+                        cS = fmaxf(fmaxf(inter, h), cV);
+                        Hv[r] = h;
+                    }
+                    Sv[r] = cS;
+                }
+                botS = cS;
+                botV = cV;
+                if (TRACE) {
+                    uint32_t *dst = trace + ((size_t)(j - j0 - 1) * 32 + lane) * W;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) dst[w] = tw[w];
+                } else {
+                    if (lane == lastlane) {
+                        float last = Sv[S - 1];
+#pragma unroll
+                        for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
+                        if (last > best) { best = last; bestj = j; }   // strict >: first maximum wins (dp_scout.h:175)
+                    }
+                    if ((j & (ALIGN_CKPT - 1)) == 0) {
+                        const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { ckS[o + r] = Sv[r]; ckH[o + r] = Hv[r]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) lutc[k] = lutn[k];
+            code_nx = code_nx2;
+        }
+    }
+};
+
+struct TaskGeom {
+    int t, N, f, L, nl, lastlane, kL;
+    const uint16_t *codes;
+    const float *lut, *col0;
+};
+
+template <int K, int S>
+__device__ __forceinline__ TaskGeom task_geom(const AlignBatch &b, int t) {
+    constexpr int R = K * S;
+    TaskGeom g;
+    g.t = t;
+    const int sg = b.task_sig[t];
+    g.f = b.task_flank[t];
+    g.N = (int)(b.sig_off[sg + 1] - b.sig_off[sg]);
+    g.codes = b.codes + b.sig_off[sg];
+    g.L = (b.flank_off[g.f + 1] - b.flank_off[g.f]) * b.samples;
+    g.nl = (g.L + R - 1) / R;
+    g.lastlane = (g.L - 1) / R;
+    g.kL = ((g.L - 1) % R) / S;
+    g.lut = b.lut + (size_t)t * b.lut_task_stride;
+    g.col0 = b.col0 + (size_t)g.f * b.col0_stride;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 1: score scan.  Single-warp CTAs pull tasks (longest first) from a global queue.
+// ---------------------------------------------------------------------------------------------
+template <int K, int S>
+__global__ void __launch_bounds__(32) align_scan_kernel(AlignBatch b, AlignGroup grp) {
+    constexpr int R = K * S;
+    const int lane = threadIdx.x;
+    const float INF = STRIQUE_SEQAN_INF;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(b.queue + 0, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= grp.n_tasks) break;
+        const TaskGeom g = task_geom<K, S>(b, grp.order[q]);
+        float Sv[R], Hv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r + 1;
+            Sv[r] = i <= g.L ? g.col0[i] : 0.f;
+            Hv[r] = INF;
+        }
+        const float diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
+        float best = INF;
+        int bestj = -1;
+        if (lane == g.lastlane && g.col0[g.L] > INF) { best = g.col0[g.L]; bestj = 0; }
+        float *ck = b.ckpt + b.ckpt_off[g.t];
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        Sweep<K, S, false>::run(g.codes, g.N, g.lut, 0, g.N, lane, g.nl, b.p, Sv, Hv, diag0, g.lastlane, g.kL, best,
+                                bestj, ck, ck + b.ckpt_rows, b.ckpt_rows, nullptr, -1, d0, d1, d2);
+        if (lane == g.lastlane) {
+            b.res[g.t].score = best;
+            b.res[g.t].best_j = bestj;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 2: blockwise trace recomputation + SeqAn traceback (dp_traceback_impl.h:377-481,496-547).
+// ---------------------------------------------------------------------------------------------
+template <int K, int S>
+__device__ __forceinline__ unsigned trace_at(const uint32_t *trace, int j0, int j, int i) {
+    constexpr int R = K * S;
+    constexpr int W = (R + 7) / 8;
+    if (i <= 0 || j <= 0) return 0u;   // DP row 0 carries no trace; column 0 is never followed
+    const int li = (i - 1) / R, r = (i - 1) % R;
+    const uint32_t w = __ldcg(trace + ((size_t)(j - j0 - 1) * 32 + li) * W + r / 8);
+    const unsigned nib = (w >> (4 * (r % 8))) & 15u;
+    const unsigned src = nib & 3u;
+    return (src == 0 ? T_DIAG : (src == 1 ? T_MAXV : T_MAXH)) | ((nib & 4u) ? T_HOPEN : T_HOR) |
+           ((nib & 8u) ? T_VOPEN : T_VER);
+}
+
+__device__ __forceinline__ int nearest_signal_index(const int32_t *rows, int L, int N, int q) {
+    // argmin_p |a_idx[p] - b_idx[q]| with first-minimum ties (numpy argmin, S.py:540-547),
+    // expressed on the per-flank-sample records (see align.cuh / DESIGN.md).
+    const int rec = rows[q];
+    const int j = rec >> 1;
+    if (!(rec & 1)) return j - 1;            // aligned to signal sample j-1: exact hit
+    int qs = q, qe = q;                      // maximal run of vertical gaps around q
+    while (qs > 0 && rows[qs - 1] == rec) --qs;
+    while (qe < L - 1 && rows[qe + 1] == rec) ++qe;
+    const int dprev = q - qs + 1, dnext = qe - q + 1;
+    const bool has_prev = j >= 1, has_next = j < N;
+    if (has_prev && (!has_next || dprev <= dnext)) return j - 1;
+    return j;
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGroup grp) {
+    constexpr int R = K * S;
+    constexpr int W = (R + 7) / 8;
+    const int lane = threadIdx.x;
+    const float INF = STRIQUE_SEQAN_INF;
+    uint32_t *trace = b.trace + (size_t)blockIdx.x * ALIGN_CKPT * 32 * W;
+    enum { ST_MAIN = 0, ST_VRUN = 1, ST_HRUN = 2 };
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(b.queue + 1, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= grp.n_tasks) break;
+        const TaskGeom g = task_geom<K, S>(b, grp.order[q]);
+        int32_t *rows = b.rows + (size_t)g.t * b.rows_stride;
+        const int bj = b.res[g.t].best_j;
+        int n_blocks = 0;
+        // traceback cursor (meaningful in lane 0).  bj < 0: no last-row score ever exceeded SeqAn's
+        // "infinity" -> traceback starts at (0,0) and every flank sample is a trailing vertical gap
+        // behind all N signal samples; bj == 0: best cell in DP column 0 -> all leading gaps.
+        int tj = bj < 0 ? g.N : bj, ti = g.L;
+        if (bj > 0) {
+            unsigned tv = 0;
+            int state = ST_MAIN;
+            bool first = true;
+            int blk = (bj - 1) / ALIGN_CKPT;
+            int j1 = bj;
+            for (;;) {
+                const int j0 = blk * ALIGN_CKPT;
+                float Sv[R], Hv[R];
+                float diag0;
+                if (blk == 0) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = lane * R + r + 1;
+                        Sv[r] = i <= g.L ? g.col0[i] : 0.f;
+                        Hv[r] = INF;
+                    }
+                    diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
+                } else {
+                    const float *ckS = b.ckpt + b.ckpt_off[g.t] + (size_t)(blk - 1) * 2 * b.ckpt_rows;
+                    const float *ckH = ckS + b.ckpt_rows;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = lane * R + r + 1;
+                        Sv[r] = ckS[i];
+                        Hv[r] = ckH[i];
+                    }
+                    diag0 = lane == 0 ? 0.f : ckS[lane * R];
+                }
+                float capS = 0.f, capH = 0.f, capV = 0.f, dummy_best = 0.f;
+                int dummy_j = 0;
+                Sweep<K, S, true>::run(g.codes, g.N, g.lut, j0, j1, lane, g.nl, b.p, Sv, Hv, diag0, g.lastlane, g.kL,
+                                       dummy_best, dummy_j, nullptr, nullptr, 0, trace, first ? bj : -1, capS, capH,
+                                       capV);
+                ++n_blocks;
+                __syncwarp();
+                if (first) {
+                    capS = __shfl_sync(0xffffffffu, capS, g.lastlane);
+                    capH = __shfl_sync(0xffffffffu, capH, g.lastlane);
+                    capV = __shfl_sync(0xffffffffu, capV, g.lastlane);
+                }
+                int done = 0;
+                if (lane == 0) {
+                    bool need_fetch = false;
+                    if (first) {
+                        tv = trace_at<K, S>(trace, j0, tj, ti);
+                        // _correctTraceValue (dp_algorithm_impl.h:1168-1185)
+                        if (capV == capS) tv = (tv & ~T_DIAG) | T_MAXV;
+                        else if (capH == capS) tv = (tv & ~T_DIAG) | T_MAXH;
+                        // _retrieveInitialTraceDirection, PreferGapsAtEnd (dp_traceback_impl.h:456-481)
+                        if (tv & T_MAXV) tv &= (T_VER | T_VOPEN | T_MAXV);
+                        else if (tv & T_MAXH) tv &= (T_HOR | T_HOPEN | T_MAXH);
+                    } else {
+                        need_fetch = true;   // paused on a cell of this (earlier) block
+                    }
+                    for (;;) {
+                        if (need_fetch) {
+                            if (tj <= j0 && tj > 0 && ti > 0) break;   // cell lies in an earlier block
+                            tv = trace_at<K, S>(trace, j0, tj, ti);
+                            need_fetch = false;
+                        }
+                        if (state == ST_MAIN) {
+                            if (!(tj > 0 && ti > 0 && tv != 0)) { done = 1; break; }
+                            if (tv & T_DIAG) {
+                                rows[ti - 1] = tj << 1; --tj; --ti; need_fetch = true;
+                            } else if ((tv & T_MAXV) && (tv & T_VER)) {
+                                state = ST_VRUN;
+                            } else if ((tv & T_MAXV) && (tv & T_VOPEN)) {
+                                rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
+                            } else if ((tv & T_MAXH) && (tv & T_HOR)) {
+                                state = ST_HRUN;
+                            } else if ((tv & T_MAXH) && (tv & T_HOPEN)) {
+                                --tj; need_fetch = true;
+                            } else { done = 1; break; }
+                        } else if (state == ST_VRUN) {
+                            const bool cont = (!(tv & T_VOPEN) || (tv & T_VER)) && ti != 1;
+                            rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
+                            if (!cont) state = ST_MAIN;
+                        } else {
+                            const bool cont = (!(tv & T_HOPEN) || (tv & T_HOR)) && tj != 1;
+                            --tj; need_fetch = true;
+                            if (!cont) state = ST_MAIN;
+                        }
+                    }
+                }
+                done = __shfl_sync(0xffffffffu, done, 0);
+                first = false;
+                if (done || blk == 0) break;
+                --blk;
+                j1 = j0;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            // leading gaps (head) or the degenerate all-gap cases: remaining flank rows are vertical gaps
+            for (int i = ti; i >= 1; --i) rows[i - 1] = (tj << 1) | 1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            strique_align_result &r = b.res[g.t];
+            const int pre = b.task_pre[g.t], post = b.task_post[g.t];
+            r.begin0 = nearest_signal_index(rows, g.L, g.N, 0);
+            r.end0 = nearest_signal_index(rows, g.L, g.N, g.L - 1);
+            r.begin_trim = nearest_signal_index(rows, g.L, g.N, clampi(pre, 0, g.L - 1));
+            r.end_trim = nearest_signal_index(rows, g.L, g.N, clampi(g.L - 1 - post, 0, g.L - 1));
+            r.n_blocks = n_blocks;
+            r.status = 0;
+        }
+        __syncwarp();
+    }
+}
+
+template <int K, int S>
+int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
+    int grid = ctx->num_sms * ALIGN_WARPS_PER_SM;
+    if (grid > g.n_tasks) grid = g.n_tasks;
+    align_scan_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+template <int K, int S>
+int launch_trace_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, int n_warps) {
+    int grid = n_warps;
+    if (grid > g.n_tasks) grid = g.n_tasks;
+    align_trace_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+}  // namespace
+
+// (K levels per lane, S samples per level) instantiations.  S = 6 is the reference's flank
+// sampling (scripts/STRique.py:507-513 'samples'); S = 1 serves arbitrary flank vectors.
+#define STRIQUE_ALIGN_INSTANCES(X) \
+    X(2, 6) X(3, 6) X(4, 6) X(5, 6) X(6, 6) X(7, 6) X(8, 6) X(9, 6) X(10, 6) X(4, 1) X(8, 1) X(16, 1) X(32, 1)
+
+bool align_pick_kernel(int nlev, int samples, int *K, int *S) {
+    if (samples == 6) {
+        for (int k = 2; k <= 10; ++k)
+            if (k * 32 >= nlev) { *K = k; *S = 6; return true; }
+    }
+    const int rows = nlev * samples;
+    const int ks[4] = {4, 8, 16, 32};
+    for (int i = 0; i < 4; ++i)
+        if (ks[i] * 32 >= rows) { *K = ks[i]; *S = 1; return true; }
+    return false;
+}
+
+int align_launch_scan(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
+#define X(k, s) \
+    if (g.K == k && g.S == s) return launch_scan_t<k, s>(ctx, b, g);
+    STRIQUE_ALIGN_INSTANCES(X)
+#undef X
+    FAIL(ctx, STRIQUE_EUNSUPPORTED, "no alignment kernel for this flank shape");
+}
+
+int align_launch_trace(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, int n_warps) {
+#define X(k, s) \
+    if (g.K == k && g.S == s) return launch_trace_t<k, s>(ctx, b, g, n_warps);
+    STRIQUE_ALIGN_INSTANCES(X)
+#undef X
+    FAIL(ctx, STRIQUE_EUNSUPPORTED, "no alignment kernel for this flank shape");
+}
+
+int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t *task_K, const int32_t *task_S,
+                           int n_tasks) {
+    if (n_tasks == 0) return STRIQUE_OK;
+    if (n_tasks > 65535) FAIL(ctx, STRIQUE_EINVAL, "alignment chunk larger than 65535 tasks");
+    dim3 grid(16, n_tasks);
+    align_build_lut_kernel<<<grid, 256, 0, ctx->stream>>>(b, task_K, task_S, n_tasks);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+}  // namespace strique

@@ -1,0 +1,108 @@
+"""GPU parity of boundary #1 (strique_align_batch behind strique_b200.align.align_raw) against
+the golden vectors of the compiled reference aligner and against the oracle on seeded inputs.
+Bit-exact: fp32 score, every view position, and the four __detect_range__ indices."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_path as rp
+from strique_b200 import align as sa
+from . import align_cases as ac
+from .conftest import C9_PREFIX, C9_SUFFIX
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'align_golden.npz')
+
+
+def _set(al, ps):
+    al.gap_open_h, al.gap_open_v, al.gap_extension_h, al.gap_extension_v, al.dist_offset, al.dist_min = ps
+
+
+def test_golden_vectors_of_compiled_reference(ctx):
+    g = np.load(GOLDEN)
+    n = int(g['n'])
+    for ps in ac.PARAM_SETS:
+        al = sa.align_raw(ctx)
+        _set(al, ps)
+        ks = [k for k in range(n) if tuple(g['params_%d' % k]) == ps]
+        got = al.align_overlap_batch([(g['a_%d' % k], g['b_%d' % k]) for k in ks])
+        for k, (score, a_idx, b_idx) in zip(ks, got):
+            assert np.float32(score) == g['score_%d' % k], k
+            assert np.array_equal(a_idx, g['a_idx_%d' % k]), k
+            assert np.array_equal(b_idx, g['b_idx_%d' % k]), k
+
+
+def test_seeded_cases_against_oracle_with_trims(ctx):
+    c = rp.CAligner()
+    for ps in ac.PARAM_SETS:
+        al = sa.align_raw(ctx)
+        _set(al, ps)
+        _set(c, ps)
+        cs = [(a, b) for p, a, b in ac.cases(seed=77, n=300, max_L=200, max_N=1500) if p == ps]
+        got = al.align_overlap_batch(cs)
+        for (a, b), (score, a_idx, b_idx) in zip(cs, got):
+            s0, a0, b0 = c.align_overlap(a, b)
+            assert np.float32(score) == np.float32(s0)
+            assert np.array_equal(a_idx, a0) and np.array_equal(b_idx, b0)
+
+
+def test_detect_range_indices_on_device(ctx, model_file):
+    """begin/end indices computed by the traceback kernel == numpy argmin over the oracle's view positions."""
+    pm = rp.PoreModel(model_file)
+    c = rp.CAligner()
+    ps = ac.PARAM_SETS[0]
+    _set(c, ps)
+    rng = np.random.default_rng(3)
+    flanks = [pm.generate_signal(C9_PREFIX, samples=6), pm.generate_signal(C9_SUFFIX, samples=6)]
+    sigs = []
+    for n in (20, 60):
+        seq = ''.join(rng.choice(list('ACGT'), 300)) + C9_PREFIX + 'GGCCCC' * n + C9_SUFFIX + ''.join(rng.choice(list('ACGT'), 300))
+        raw = pm.generate_signal(seq, samples=8, noise=True, rng=rng)
+        morph, _ = rp.condition(pm, raw)
+        sigs.append(morph)
+    codes, vals, off = [], [], [0]
+    for s in sigs:
+        cc, vv = sa.encode_signal(s)
+        assert len(vv) <= 256
+        v = np.zeros(256, np.float32); v[:len(vv)] = vv
+        codes.append(cc.astype(np.uint8)); vals.append(v); off.append(off[-1] + len(cc))
+    levels = [sa.run_length_levels(f) for f in flanks]
+    assert all(s == 6 for _, s in levels)
+    flank_off = np.cumsum([0] + [len(l) for l, _ in levels])
+    tasks = [(si, fi) for si in range(len(sigs)) for fi in range(2)]
+    pre = [600 if fi == 0 else 0 for _, fi in tasks]
+    post = [0 if fi == 0 else 600 for _, fi in tasks]
+    res = ctx.align_batch(ps, np.concatenate(codes), off, np.stack(vals), np.concatenate([l for l, _ in levels]),
+                          flank_off, 6, [t[0] for t in tasks], [t[1] for t in tasks], pre, post)
+    for k, (si, fi) in enumerate(tasks):
+        s0, a0, b0 = c.align_overlap(sigs[si], flanks[fi])
+        want = ac.detect_range_indices(a0, b0, pre[k], post[k])
+        assert np.float32(res['score'][k]) == np.float32(s0)
+        assert (res['begin0'][k], res['end0'][k], res['begin_trim'][k], res['end_trim'][k]) == want
+        assert res['n_blocks'][k] >= 2      # 870 flank samples span more than one 512-column block
+
+
+def test_long_signal_score_only_property(ctx):
+    """At a size where the oracle's full trace matrix is heavy: score and end column against the
+    oracle's score-only scan, plus the planted flank position."""
+    rng = np.random.default_rng(9)
+    lev = np.round(rng.uniform(60, 120, 145), 2)
+    b = np.repeat(lev, 6)
+    N = 120000
+    a = np.round(rng.uniform(60, 120, N))
+    start = 77777
+    planted = np.repeat(lev, rng.integers(6, 10, 145))
+    a[start:start + len(planted)] = np.round(planted)
+    c = rp.CAligner()
+    ps = ac.PARAM_SETS[0]
+    _set(c, ps)
+    al = sa.align_raw(ctx)
+    _set(al, ps)
+    cc, vv = sa.encode_signal(a)
+    v = np.zeros(256, np.float32); v[:len(vv)] = vv
+    res = ctx.align_batch(ps, cc.astype(np.uint8), [0, N], v[None], lev.astype(np.float32), [0, 145], 6, [0], [0], [0], [0])
+    s0, bj = c.score_only(a, b)
+    assert np.float32(res['score'][0]) == np.float32(s0)
+    assert res['best_j'][0] == bj
+    assert abs(res['begin0'][0] - start) <= 8 and abs(res['end0'][0] - (start + len(planted))) <= 8
