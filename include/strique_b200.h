@@ -100,6 +100,146 @@ int strique_align_batch(strique_ctx *ctx, const strique_align_params *params,
 int64_t strique_last_align_cells(const strique_ctx *ctx);
 float strique_last_scan_ms(const strique_ctx *ctx);
 
+/* ---- boundary #2: Viterbi decoding of a compiled HMM ----------------------------------------- */
+/*
+ * A "compiled" HMM (strique_b200/hmm.py builds it from the reference's topology,
+ * scripts/STRique.py:201-500): n_emit emitting states, n_chain silent chain states (profile-HMM
+ * delete states), START = index n_emit + n_chain.  All other silent states have been composed away.
+ *   in_*        : CSR in-edges of the emitting states; sources index [emitting | chain | START] and
+ *                 are read from the PREVIOUS time step
+ *   emit_kind   : 0 Normal(a = mean, b = std), 1 Uniform(a = lo, b = hi)
+ *   emit_flags  : STRIQUE_HMM_COUNT | _REPEAT | _SEP | _MOD
+ *   chain_pred_logw[c]: log weight of chain state c-1 -> c (-inf if c starts a chain)
+ *   chain_in_*  : CSR entry edges of the chain states (<= 3 each); sources are emitting states or
+ *                 START, read from the SAME time step
+ *   end_*       : edges into the END state, evaluated after the last sample
+ */
+#define STRIQUE_HMM_COUNT 1   /* visits are counted (repeatHMM d1/d2, S.py:374-378)              */
+#define STRIQUE_HMM_REPEAT 2  /* state name contains 'repeat' (S.py:608)                           */
+#define STRIQUE_HMM_SEP 4     /* s0 / e0 of repeatModHMM: separates repeat passes (S.py:496)       */
+#define STRIQUE_HMM_MOD 8     /* state name contains 'mod' (S.py:497)                              */
+
+typedef struct {
+    int32_t n_emit, n_chain;
+    const int32_t *in_ptr;
+    const int32_t *in_src;
+    const double *in_logw;
+    const int32_t *emit_kind;
+    const double *emit_a;
+    const double *emit_b;
+    const uint8_t *emit_flags;
+    const double *chain_pred_logw;
+    const int32_t *chain_in_ptr;
+    const int32_t *chain_in_src;
+    const double *chain_in_logw;
+    int32_t n_end;
+    const int32_t *end_src;
+    const double *end_logw;
+} strique_hmm_desc;
+
+typedef struct {
+    double logp;          /* Viterbi log probability (float64 like pomegranate)                    */
+    int32_t n_count;      /* visits of COUNT states on the best path                               */
+    int32_t t_first;      /* first / last sample decoded by a REPEAT state (-1: none)              */
+    int32_t t_last;
+    int32_t pattern_len;  /* number of repeat passes found between SEP states                      */
+    int32_t status;       /* 0 ok, 1 impossible sequence (log p = -inf), 2 internal error          */
+    int32_t reserved;
+} strique_viterbi_result;
+
+int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc, int32_t *model_id);
+/*
+ *   x, x_offsets : float64 samples of all sequences concatenated; [n_seq+1] offsets (host)
+ *   pattern_out  : optional, same layout as x: per sequence the '0'/'1' pattern is written
+ *                  RIGHT-aligned in its slot (last pattern_len bytes)
+ *   path_out     : optional, same layout as x: emitting state id decoding each sample
+ */
+int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_seq, const double *x, const int64_t *x_offsets,
+                          int memspace, strique_viterbi_result *results, uint8_t *pattern_out, uint16_t *path_out);
+
+/* work of the last viterbi / detect call: (time steps) x (in-edges of the model), summed */
+int64_t strique_last_viterbi_edges(const strique_ctx *ctx);
+
+/* ---- conditioning ---------------------------------------------------------------------------- */
+typedef struct {
+    double m5_mod, m95_mod;       /* medians of the model k-mer means below the 1st / above the 99th percentile */
+    double model_min, model_max;  /* pore_model.model_min / model_max (scripts/STRique.py:126-127)             */
+} strique_pore_constants;
+
+typedef struct {
+    double flt_median, flt_mad;   /* median and mean-absolute-deviation of the median-filtered read */
+    double flt_c1, flt_c2;        /* 'minmax' centre and half-range of the filtered read            */
+    double raw_c1, raw_c2;        /* same for the raw read (0,1 unless want_raw_stats)              */
+    double u8_c1, u8_c2;          /* same for the uint8 morphology signal                           */
+    double status;                /* 0 ok, 1 degenerate read (zero MAD or empty percentile tail)    */
+    double reserved[3];
+} strique_condition_stats;
+
+/*
+ * raw_kind 0: int16 samples (fast5 DAC values), 1: float64 samples.  Outputs (host, all optional):
+ *   flt_out    : median-filtered signal, same type and layout as raw
+ *   codes_out  : uint16 per sample, value 0..255: closing(opening(uint8 z-score))
+ *   values_out : [n_reads*256] fp32 value of each code after 'minmax' normalisation to the model
+ *   stats_out  : [n_reads]
+ */
+int strique_condition_batch(strique_ctx *ctx, const strique_pore_constants *pore, int n_reads, const void *raw,
+                            int raw_kind, const int64_t *raw_offsets, int want_raw_stats, void *flt_out,
+                            uint16_t *codes_out, float *values_out, strique_condition_stats *stats_out);
+
+/* ---- the whole per-read path: repeatCounter.detect, batched ---------------------------------- */
+typedef struct {
+    const float *prefix_levels;   /* k-mer means of prefix_ext (generate_signal / samples), fp32 */
+    int32_t n_prefix_levels;
+    const float *suffix_levels;
+    int32_t n_suffix_levels;
+    int32_t pre_trim;             /* len(prefix_ext) - len(prefix) in samples (S.py:598) */
+    int32_t post_trim;            /* len(suffix_ext) - len(suffix) in samples (S.py:599) */
+    int32_t count_model;          /* id from strique_hmm_create: flankedRepeatHMM          */
+    int32_t mod_model;            /* id of the repeatModHMM or -1                          */
+    int32_t count_offset;         /* flanking_count - repeat_offset (S.py:378, 437)        */
+} strique_target_desc;
+
+int strique_target_create(strique_ctx *ctx, const strique_target_desc *desc, int32_t *target_id);
+
+typedef struct {
+    strique_align_params align;
+    int32_t samples;              /* flank samples per k-mer (align config 'samples', S.py:513) */
+    int32_t use_mod;              /* run the methylation HMM (reference: --mod_model given)      */
+    strique_pore_constants pore;  /* base pore model                                             */
+    double mod_clip_lo, mod_clip_hi;  /* min / max of both models' model_min / model_max (S.py:467-468) */
+} strique_detect_config;
+
+typedef struct {
+    double score_prefix, score_suffix;   /* fp32 alignment score / (end - begin), or 0.0 (S.py:542-545) */
+    double log_p;                        /* 0 when the HMM stage did not run                             */
+    int32_t count;                       /* repeat count n                                               */
+    int32_t offset, ticks;               /* prefix_end, max(suffix_begin - prefix_end, 0)                */
+    int32_t prefix_begin, prefix_end, suffix_begin, suffix_end;
+    int32_t hmm_ran;                     /* 1 if the count HMM decoded this read                         */
+    int32_t mod_len;                     /* length of the methylation pattern; -1 means '-'              */
+    int32_t status;                      /* 0 ok, 1 degenerate read                                      */
+    int64_t mod_off;                     /* offset of the pattern in mod_out                             */
+} strique_detect_result;
+
+/*
+ * raw / raw_offsets as in strique_condition_batch; read_target[r] = id from strique_target_create.
+ * mod_out (host, capacity mod_cap bytes) receives the '0'/'1' patterns back to back.
+ */
+int strique_detect_batch(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
+                         int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
+                         strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap);
+
+/* device time of the stages of the last strique_detect_batch call (ms) */
+#define STRIQUE_STAGE_CONDITION 0
+#define STRIQUE_STAGE_ALIGN_TABLE 1
+#define STRIQUE_STAGE_ALIGN_SCAN 2
+#define STRIQUE_STAGE_ALIGN_TRACE 3
+#define STRIQUE_STAGE_VITERBI_COUNT 4
+#define STRIQUE_STAGE_VITERBI_MOD 5
+#define STRIQUE_STAGE_H2D 6
+#define STRIQUE_N_STAGES 8
+float strique_last_stage_ms(const strique_ctx *ctx, int stage);
+
 #ifdef __cplusplus
 }
 #endif

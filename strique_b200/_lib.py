@@ -23,6 +23,44 @@ class AlignParams(ctypes.Structure):
                 ('gap_open_h', 'gap_open_v', 'gap_extension_h', 'gap_extension_v', 'dist_offset', 'dist_min')]
 
 
+class PoreConstants(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ('m5_mod', 'm95_mod', 'model_min', 'model_max')]
+
+
+class HmmDesc(ctypes.Structure):
+    _fields_ = [('n_emit', ctypes.c_int32), ('n_chain', ctypes.c_int32),
+                ('in_ptr', ctypes.c_void_p), ('in_src', ctypes.c_void_p), ('in_logw', ctypes.c_void_p),
+                ('emit_kind', ctypes.c_void_p), ('emit_a', ctypes.c_void_p), ('emit_b', ctypes.c_void_p),
+                ('emit_flags', ctypes.c_void_p), ('chain_pred_logw', ctypes.c_void_p),
+                ('chain_in_ptr', ctypes.c_void_p), ('chain_in_src', ctypes.c_void_p), ('chain_in_logw', ctypes.c_void_p),
+                ('n_end', ctypes.c_int32), ('end_src', ctypes.c_void_p), ('end_logw', ctypes.c_void_p)]
+
+
+class TargetDesc(ctypes.Structure):
+    _fields_ = [('prefix_levels', ctypes.c_void_p), ('n_prefix_levels', ctypes.c_int32),
+                ('suffix_levels', ctypes.c_void_p), ('n_suffix_levels', ctypes.c_int32),
+                ('pre_trim', ctypes.c_int32), ('post_trim', ctypes.c_int32),
+                ('count_model', ctypes.c_int32), ('mod_model', ctypes.c_int32), ('count_offset', ctypes.c_int32)]
+
+
+class DetectConfig(ctypes.Structure):
+    _fields_ = [('align', AlignParams), ('samples', ctypes.c_int32), ('use_mod', ctypes.c_int32),
+                ('pore', PoreConstants), ('mod_clip_lo', ctypes.c_double), ('mod_clip_hi', ctypes.c_double)]
+
+
+VITERBI_RESULT_DTYPE = np.dtype([('logp', np.float64), ('n_count', np.int32), ('t_first', np.int32),
+                                 ('t_last', np.int32), ('pattern_len', np.int32), ('status', np.int32),
+                                 ('reserved', np.int32)])
+CONDITION_STATS_DTYPE = np.dtype([(n, np.float64) for n in
+                                  ('flt_median', 'flt_mad', 'flt_c1', 'flt_c2', 'raw_c1', 'raw_c2', 'u8_c1', 'u8_c2',
+                                   'status', 'r0', 'r1', 'r2')])
+DETECT_RESULT_DTYPE = np.dtype([('score_prefix', np.float64), ('score_suffix', np.float64), ('log_p', np.float64),
+                                ('count', np.int32), ('offset', np.int32), ('ticks', np.int32),
+                                ('prefix_begin', np.int32), ('prefix_end', np.int32), ('suffix_begin', np.int32),
+                                ('suffix_end', np.int32), ('hmm_ran', np.int32), ('mod_len', np.int32),
+                                ('status', np.int32), ('mod_off', np.int64)], align=True)
+STAGES = ('condition', 'align_table', 'align_scan', 'align_trace', 'viterbi_count', 'viterbi_mod', 'h2d')
+
 ALIGN_RESULT_DTYPE = np.dtype([('score', np.float32), ('best_j', np.int32), ('begin0', np.int32), ('end0', np.int32),
                                ('begin_trim', np.int32), ('end_trim', np.int32), ('n_blocks', np.int32),
                                ('status', np.int32)])
@@ -63,6 +101,23 @@ def load():
                                         c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int, c_void_p, c_void_p, c_int64]
+    lib.strique_last_viterbi_edges.restype = c_int64
+    lib.strique_last_viterbi_edges.argtypes = [c_void_p]
+    lib.strique_last_stage_ms.restype = ctypes.c_float
+    lib.strique_last_stage_ms.argtypes = [c_void_p, c_int]
+    lib.strique_hmm_create.restype = c_int
+    lib.strique_hmm_create.argtypes = [c_void_p, ctypes.POINTER(HmmDesc), ctypes.POINTER(ctypes.c_int32)]
+    lib.strique_viterbi_batch.restype = c_int
+    lib.strique_viterbi_batch.argtypes = [c_void_p, ctypes.c_int32, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_void_p]
+    lib.strique_condition_batch.restype = c_int
+    lib.strique_condition_batch.argtypes = [c_void_p, ctypes.POINTER(PoreConstants), c_int, c_void_p, c_int, c_void_p,
+                                            c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.strique_target_create.restype = c_int
+    lib.strique_target_create.argtypes = [c_void_p, ctypes.POINTER(TargetDesc), ctypes.POINTER(ctypes.c_int32)]
+    lib.strique_detect_batch.restype = c_int
+    lib.strique_detect_batch.argtypes = [c_void_p, ctypes.POINTER(DetectConfig), c_int, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_int, c_void_p, c_void_p, c_int64]
     _lib = lib
     return lib
 
@@ -156,6 +211,91 @@ class Context:
                                           _ptr(task_post_trim), memspace, _ptr(results), _ptr(rows), stride)
         self.check(rc, 'strique_align_batch')
         return (results, rows) if want_rows else results
+
+
+    # -- boundary #2 ------------------------------------------------------------------------------
+    def hmm_create(self, c):
+        """Register a compiled HMM (strique_b200.hmm.CompiledHMM) -> model id."""
+        keep = [np.ascontiguousarray(a) for a in (c.in_ptr, c.in_src, c.in_logw, c.emit_kind, c.emit_a, c.emit_b,
+                                                  c.emit_flags, c.chain_pred_logw, c.chain_in_ptr, c.chain_in_src,
+                                                  c.chain_in_logw, c.end_src, c.end_logw)]
+        d = HmmDesc(c.n_emit, c.n_chain, *[a.ctypes.data for a in keep[:11]], len(c.end_src),
+                    keep[11].ctypes.data, keep[12].ctypes.data)
+        mid = ctypes.c_int32(-1)
+        self.check(self.lib.strique_hmm_create(self.handle, ctypes.byref(d), ctypes.byref(mid)), 'strique_hmm_create')
+        return mid.value
+
+    def viterbi_batch(self, model_id, sequences, want_path=False):
+        """sequences: list of float64 vectors -> (results, patterns[, paths])."""
+        seqs = [np.ascontiguousarray(x, dtype=np.float64) for x in sequences]
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(x) for x in seqs])
+        x = np.concatenate(seqs) if seqs else np.zeros(0)
+        res = np.zeros(len(seqs), dtype=VITERBI_RESULT_DTYPE)
+        pat = np.zeros(max(1, len(x)), dtype=np.uint8)
+        path = np.zeros(max(1, len(x)), dtype=np.uint16) if want_path else None
+        self.check(self.lib.strique_viterbi_batch(self.handle, model_id, len(seqs), _ptr(x), _ptr(off), HOST,
+                                                  _ptr(res), _ptr(pat), _ptr(path)), 'strique_viterbi_batch')
+        patterns = []
+        for k in range(len(seqs)):
+            n = int(res['pattern_len'][k])
+            patterns.append(pat[off[k + 1] - n:off[k + 1]].tobytes().decode('ascii') if res['status'][k] == 0 else None)
+        if want_path:
+            return res, patterns, [path[off[k]:off[k + 1]].copy() for k in range(len(seqs))]
+        return res, patterns
+
+    # -- conditioning ------------------------------------------------------------------------------
+    @staticmethod
+    def _pack_raw(signals):
+        sigs = [np.asarray(s) for s in signals]
+        kind = 0 if all(s.dtype == np.int16 for s in sigs) else 1
+        dt = np.int16 if kind == 0 else np.float64
+        off = np.zeros(len(sigs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(s) for s in sigs])
+        raw = np.concatenate([s.astype(dt, copy=False) for s in sigs]) if sigs else np.zeros(0, dt)
+        return np.ascontiguousarray(raw), off, kind
+
+    def condition_batch(self, pore, signals, want_raw_stats=False):
+        raw, off, kind = self._pack_raw(signals)
+        n = len(off) - 1
+        flt = np.zeros_like(raw)
+        codes = np.zeros(len(raw), dtype=np.uint16)
+        vals = np.zeros((n, 256), dtype=np.float32)
+        stats = np.zeros(n, dtype=CONDITION_STATS_DTYPE)
+        pc = PoreConstants(*pore)
+        self.check(self.lib.strique_condition_batch(self.handle, ctypes.byref(pc), n, _ptr(raw), kind, _ptr(off),
+                                                    1 if want_raw_stats else 0, _ptr(flt), _ptr(codes), _ptr(vals),
+                                                    _ptr(stats)), 'strique_condition_batch')
+        return flt, codes, vals, stats, off
+
+    # -- whole path ----------------------------------------------------------------------------------
+    def target_create(self, prefix_levels, suffix_levels, pre_trim, post_trim, count_model, mod_model, count_offset):
+        pl = np.ascontiguousarray(prefix_levels, dtype=np.float32)
+        sl = np.ascontiguousarray(suffix_levels, dtype=np.float32)
+        d = TargetDesc(pl.ctypes.data, len(pl), sl.ctypes.data, len(sl), pre_trim, post_trim, count_model, mod_model,
+                       count_offset)
+        tid = ctypes.c_int32(-1)
+        self.check(self.lib.strique_target_create(self.handle, ctypes.byref(d), ctypes.byref(tid)), 'strique_target_create')
+        return tid.value
+
+    def detect_batch(self, cfg, raw, raw_offsets, raw_kind, read_target, memspace=HOST):
+        raw_offsets = np.ascontiguousarray(raw_offsets, dtype=np.int64)
+        read_target = np.ascontiguousarray(read_target, dtype=np.int32)
+        n = len(read_target)
+        res = np.zeros(n, dtype=DETECT_RESULT_DTYPE)
+        cap = int(raw_offsets[-1] // 8 + 64 * n + 64) if cfg.use_mod else 0
+        mod = np.zeros(max(cap, 1), dtype=np.uint8)
+        self.check(self.lib.strique_detect_batch(self.handle, ctypes.byref(cfg), n, _ptr(raw), raw_kind, _ptr(raw_offsets),
+                                                 _ptr(read_target), memspace, _ptr(res), _ptr(mod), cap),
+                   'strique_detect_batch')
+        return res, mod
+
+    def stage_ms(self):
+        return {name: float(self.lib.strique_last_stage_ms(self.handle, i)) for i, name in enumerate(STAGES)}
+
+    @property
+    def last_viterbi_edges(self):
+        return int(self.lib.strique_last_viterbi_edges(self.handle))
 
 
 _default_ctx = {}

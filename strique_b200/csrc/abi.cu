@@ -6,12 +6,18 @@
 #include <numeric>
 
 #include "align.cuh"
+#include "pipeline.cuh"
 
 std::string g_strique_create_error;
 
 strique_ctx::~strique_ctx() {
     for (auto &kv : bufs)
         if (kv.second.p) cudaFree(kv.second.p);
+    for (void *p : owned) cudaFree(p);
+    for (auto *m : models) delete m;
+    for (auto *t : targets) delete t;
+    for (auto &e : stage_ev)
+        if (e) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -214,7 +220,9 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         b.res = d_res.as<strique_align_result>(); b.queue = d_queue.as<int>();
         b.lut_fix = d_fix.as<unsigned long long>(); b.lut_fix_cap = fix_cap;
 
+        stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TABLE);
         TRY(align_launch_build_lut(ctx, b, d_tK.as<int32_t>(), d_tS.as<int32_t>(), n));
+        stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TABLE + 1);
         // ---- patch table entries too close to an fp32 rounding midpoint with libm's pow -------
         CUDA_TRY(ctx, cudaMemcpyAsync(fix_host.data(), d_fix.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -269,10 +277,12 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         // ---- pass 2: trace blocks + traceback -------------------------------------------------
+        stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TRACE);
         for (const AlignGroup &g : groups) {
             CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
             TRY(align_launch_trace(ctx, b, g, trace_warps));
         }
+        stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TRACE + 1);
         if (results_host)
             CUDA_TRY(ctx, cudaMemcpyAsync(results_host + t0, d_res.p, (size_t)n * sizeof(strique_align_result), cudaMemcpyDeviceToHost, ctx->stream));
         if (results_dev_out)
@@ -285,6 +295,9 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         scan_ms_total += ms;
+        ctx->stage_ms[STRIQUE_STAGE_ALIGN_SCAN] += ms;
+        stage_collect(ctx, STRIQUE_STAGE_ALIGN_TABLE);
+        stage_collect(ctx, STRIQUE_STAGE_ALIGN_TRACE);
         t0 = t1;
     }
     ctx->last_align_cells = cells_total;
@@ -312,6 +325,7 @@ extern "C" int strique_align_batch(strique_ctx *ctx, const strique_align_params 
         !task_pre_trim || !task_post_trim || !results)
         FAIL(ctx, STRIQUE_EINVAL, "strique_align_batch: null pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    stage_reset(ctx);
     const int64_t total = sig_offsets[n_signals];
     const int total_lev = flank_offsets[n_flanks];
     DevBuf &d_in8 = ctx->buf("ab.in8"), &d_codes = ctx->buf("ab.codes"), &d_sigoff = ctx->buf("ab.sigoff"),

@@ -18,6 +18,10 @@
 #define STRIQUE_SEQAN_INF 5.87747175411143754e-39f
 
 struct strique_ctx;
+namespace strique {
+struct HmmModel;
+struct Target;
+}
 
 // A growable device buffer owned by the context (looked up by name, reused across calls).
 struct DevBuf {
@@ -39,7 +43,13 @@ struct strique_ctx {
     // statistics of the last alignment call
     int64_t last_align_cells = 0;
     float last_scan_ms = 0.f;
+    int64_t last_viterbi_edges = 0;
+    float stage_ms[8] = {0};              // last detect call: see STRIQUE_STAGE_* in the public header
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t stage_ev[16] = {nullptr};
+    std::vector<void *> owned;            // device allocations living as long as the context (models)
+    std::vector<strique::HmmModel *> models;
+    std::vector<strique::Target *> targets;
     std::map<std::string, DevBuf> bufs;   // persistent device scratch
     DevBuf &buf(const char *name) { return bufs[name]; }
     ~strique_ctx();
@@ -92,3 +102,20 @@ inline int DevBuf::ensure(strique_ctx *ctx, size_t bytes) {
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// per-stage device timing: events 2*stage (begin) and 2*stage+1 (end) on the context's stream
+static inline void stage_mark(strique_ctx *ctx, int idx) {
+    if (!ctx->stage_ev[idx]) cudaEventCreate(&ctx->stage_ev[idx]);
+    cudaEventRecord(ctx->stage_ev[idx], ctx->stream);
+}
+static inline void stage_collect(strique_ctx *ctx, int stage) {   // call after a stream synchronize
+    float ms = 0.f;
+    if (ctx->stage_ev[2 * stage] && ctx->stage_ev[2 * stage + 1] &&
+        cudaEventElapsedTime(&ms, ctx->stage_ev[2 * stage], ctx->stage_ev[2 * stage + 1]) == cudaSuccess)
+        ctx->stage_ms[stage] += ms;
+    else
+        cudaGetLastError();
+}
+static inline void stage_reset(strique_ctx *ctx) {
+    for (int i = 0; i < 8; ++i) ctx->stage_ms[i] = 0.f;
+}

@@ -1,0 +1,89 @@
+"""GPU parity of the whole per-read path (strique_detect_batch behind strique_b200.repeatCounter)
+against the oracle pipeline: integer outputs bit-exact, alignment scores exact (fp32 score /
+integer), log p within 1e-9 relative.  Includes the reference's own unit-test assertions
+(scripts/STRique_test.py: n == i) and the documented offset/ticks of the bundled read."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_path as rp
+from strique_b200 import fast5
+from strique_b200.counter import repeatCounter
+from . import synth
+from .conftest import C9_PREFIX, C9_SUFFIX, FMR1_PREFIX, FMR1_SUFFIX, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, want):
+    assert got[0] == want[0]
+    assert got[1] == want[1] and got[2] == want[2]
+    assert got[3] == pytest.approx(want[3], rel=1e-9)
+    assert got[4:] == tuple(int(x) if not isinstance(x, str) else x for x in want[4:])
+
+
+def test_reference_unit_test_recipes(ctx, model_file):
+    """scripts/STRique_test.py:45-101 with a seeded backbone: noise-free samples=8 signals, n == i."""
+    pm = rp.PoreModel(model_file)
+    rng = np.random.default_rng(1)
+    dt = repeatCounter(model_file, context=ctx)
+    dt.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)
+    dt.add_target('fmr1', 'GCG', FMR1_PREFIX, FMR1_SUFFIX)
+    ref = rp.RefRepeatCounter(model_file)
+    ref.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)
+    ref.add_target('fmr1', 'GCG', FMR1_PREFIX, FMR1_SUFFIX)
+    bb = synth.backbone(rng, 2000)
+    items, expect = [], []
+    for i in (100, 200, 300):
+        items.append(('c9orf72', pm.generate_signal(bb[:1000] + C9_PREFIX + 'GGCCCC' * i + C9_SUFFIX + bb[-1000:], samples=8), '+'))
+        expect.append(i)
+        items.append(('fmr1', pm.generate_signal(bb[:1000] + FMR1_PREFIX + 'GCG' * i + FMR1_SUFFIX + bb[-1000:], samples=8), '+'))
+        expect.append(i)
+    for i in range(10, 100, 20):
+        items.append(('c9orf72', pm.generate_signal(C9_PREFIX + 'GGCCCC' * i + C9_SUFFIX, samples=8), '+'))
+        expect.append(i)
+    got = dt.detect_batch(items)
+    for (name, sig, strand), g, n in zip(items, got, expect):
+        assert g[0] == n
+        _same(g, ref.detect(name, sig, strand))
+    with pytest.raises(ValueError):
+        dt.detect('nope', items[0][1], '+')
+    with pytest.raises(ValueError):
+        dt.detect('c9orf72', items[0][1], '*')
+    with pytest.raises(ValueError):
+        dt.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)
+
+
+def test_noisy_int16_reads_both_strands_with_methylation(ctx, model_file, mod_model_file):
+    pm, pm_mod = rp.PoreModel(model_file), rp.PoreModel(mod_model_file)
+    rng = np.random.default_rng(2)
+    dt = repeatCounter(model_file, mod_model_file=mod_model_file, context=ctx)
+    dt.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)
+    ref = rp.RefRepeatCounter(model_file, mod_model_file=mod_model_file)
+    ref.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)
+    items = []
+    for n, strand, model in [(12, '+', pm), (35, '-', pm), (70, '+', pm_mod), (150, '-', pm_mod), (2, '+', pm)]:
+        seq = synth.read_sequence(rng, C9_PREFIX, 'GGCCCC', C9_SUFFIX, n, flank=500, strand=strand)
+        items.append(('c9orf72', synth.simulate(model, seq, rng, noise=True, int16=True), strand))
+    # a read without the locus: the HMM stage must be skipped exactly like the reference does
+    items.append(('c9orf72', synth.simulate(pm, synth.backbone(rng, 1500), rng, noise=True, int16=True), '+'))
+    got = dt.detect_batch(items)
+    for (name, sig, strand), g in zip(items, got):
+        _same(g, ref.detect(name, sig, strand))
+    assert got[2][6].count('1') > got[0][6].count('1')
+
+
+def test_bundled_c9orf72_read(ctx, model_file):
+    """data/c9orf72.fast5, minus strand: documented offset 1633 / ticks 40758
+    (docs/installation/test.md:16); the remaining columns equal the oracle's."""
+    raw = fast5.read_raw_signal(os.path.join(ROOT, 'data', 'c9orf72.fast5'))
+    cols = open(os.path.join(ROOT, 'configs', 'repeat_config.tsv')).read().split('\n')[1].split()
+    dt = repeatCounter(model_file, context=ctx)
+    dt.add_target(cols[3], cols[4], cols[5], cols[6])
+    got = dt.detect('c9orf72', raw, '-')
+    assert got[4] == 1633 and got[5] == 40758
+    assert got[0] == 733
+    assert got[1] == 6.358286602121677 and got[2] == 6.086084196539416
+    assert got[3] == pytest.approx(-121549.34988420883, rel=1e-9)
+    assert got[6] == '-'
