@@ -148,6 +148,9 @@ typedef struct {
 } strique_viterbi_result;
 
 int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc, int32_t *model_id);
+/* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, otherwise the team
+ * kernel shape as wps*1000 + high_slots*100 + low_slots*10 + chain_slots (diagnostic) */
+int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id);
 /*
  *   x, x_offsets : float64 samples of all sequences concatenated; [n_seq+1] offsets (host)
  *   pattern_out  : optional, same layout as x: per sequence the '0'/'1' pattern is written

@@ -107,6 +107,8 @@ def load():
     lib.strique_last_stage_ms.argtypes = [c_void_p, c_int]
     lib.strique_hmm_create.restype = c_int
     lib.strique_hmm_create.argtypes = [c_void_p, ctypes.POINTER(HmmDesc), ctypes.POINTER(ctypes.c_int32)]
+    lib.strique_hmm_kernel_shape.restype = c_int
+    lib.strique_hmm_kernel_shape.argtypes = [c_void_p, ctypes.c_int32]
     lib.strique_viterbi_batch.restype = c_int
     lib.strique_viterbi_batch.argtypes = [c_void_p, ctypes.c_int32, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                           c_void_p, c_void_p]
@@ -224,6 +226,10 @@ class Context:
         mid = ctypes.c_int32(-1)
         self.check(self.lib.strique_hmm_create(self.handle, ctypes.byref(d), ctypes.byref(mid)), 'strique_hmm_create')
         return mid.value
+
+    def hmm_kernel_shape(self, model_id):
+        """0: generic Viterbi kernel; else team-kernel shape wps*1000 + nh*100 + nl*10 + qc."""
+        return int(self.lib.strique_hmm_kernel_shape(self.handle, model_id))
 
     def viterbi_batch(self, model_id, sequences, want_path=False):
         """sequences: list of float64 vectors -> (results, patterns[, paths])."""

@@ -1,6 +1,8 @@
 // Alignment kernels (see align.cuh for the design summary).
 #include "align.cuh"
 
+#include <math.h>
+
 namespace strique {
 
 namespace {
@@ -166,6 +168,99 @@ struct Sweep {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Score scan for LINEAR gap costs (gap_open == gap_extension in both directions -- the reference's
+// own configuration, scripts/STRique.py:507-512 and configs/STRique.json).  Then, bit for bit,
+//     H[j][i] = max(H[j-1][i] + g_h, S[j-1][i] + g_h) = S[j-1][i] + g_h        for j >= 2
+//     V[j][i] = max(V[j][i-1] + g_v, S[j][i-1] + g_v) = S[j][i-1] + g_v        for j >= 1
+// because S >= H and S >= V in every computed cell and fp32 rounding is monotonic
+// (max(fl(a+g), fl(b+g)) == fl(max(a,b)+g)).  The exceptions are SeqAn's initial "infinity":
+// H of DP column 0 is the positive denormal INF > S, handled in the j == 1 column, and V of DP row
+// 0 is INF > S[j][0] = 0, where INF + g_v == 0 + g_v exactly (the host checks |g| >= 1e-20).
+// The cell is 3 FADD + one 3-input FMNMX, no H / V state: half the registers of the affine sweep.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+template <int K, int S>
+struct LinSweep {
+    static constexpr int R = K * S;
+
+    template <bool FIRST, bool CK>
+    __device__ __forceinline__ static float column(float (&Sv)[R], const float (&lutc)[K], float diag, float cS,
+                                                   const float gh, const float gv, float *__restrict__ ckS,
+                                                   float *__restrict__ ckH) {
+        const float INF = STRIQUE_SEQAN_INF;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float pS = Sv[r];
+            const float inter = diag + lutc[r / S];
+            diag = pS;
+            const float h = (FIRST ? fmaxf(INF, pS) : pS) + gh;
+            const float v = cS + gv;
+            cS = fmax3(inter, h, v);
+            Sv[r] = cS;
+            if (CK) { ckS[r] = cS; ckH[r] = h; }
+        }
+        return cS;
+    }
+
+    __device__ __forceinline__ static void run(const uint16_t *__restrict__ codes, const int N,
+                                               const float *__restrict__ lut, const int lane, const int nl,
+                                               const strique_align_params &p, float (&Sv)[R], float diag_next,
+                                               const int lastlane, const int kL, float &best, int &bestj,
+                                               float *__restrict__ ckS, float *__restrict__ ckH, const int ckpt_rows) {
+        const float gh = p.gap_extension_h, gv = p.gap_extension_v;
+        const int row_len = 32 * K;
+        float lutc[K], lutn[K];
+        float botS = 0.f;
+        const int last_step = N + nl - 1;
+        {
+            const int c = codes[clampi(-lane, 0, N - 1)];
+            const float *row = lut + (size_t)c * row_len + lane * K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
+        }
+        int code_nx = codes[clampi(1 - lane, 0, N - 1)];
+        for (int s = 1; s <= last_step; ++s) {
+            const int j = s - lane;
+            {
+                const float *row = lut + (size_t)code_nx * row_len + lane * K;
+#pragma unroll
+                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k);
+            }
+            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
+            float inS = __shfl_up_sync(0xffffffffu, botS, 1);
+            if (lane == 0) inS = 0.f;            // DP row 0: free begin, S = 0
+            if (j > 0 && j <= N && lane < nl) {
+                const float diag = diag_next;
+                diag_next = inS;
+                if (j == 1) {
+                    botS = column<true, false>(Sv, lutc, diag, inS, gh, gv, nullptr, nullptr);
+                } else if ((j & (ALIGN_CKPT - 1)) == 0) {
+                    const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
+                    botS = column<false, true>(Sv, lutc, diag, inS, gh, gv, ckS + o, ckH + o);
+                } else {
+                    botS = column<false, false>(Sv, lutc, diag, inS, gh, gv, nullptr, nullptr);
+                }
+                if (lane == lastlane) {
+                    float last = Sv[S - 1];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
+                    if (last > best) { best = last; bestj = j; }   // strict >: first maximum wins (dp_scout.h:175)
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) lutc[k] = lutn[k];
+            code_nx = code_nx2;
+        }
+    }
+};
+
 struct TaskGeom {
     int t, N, f, L, nl, lastlane, kL;
     const uint16_t *codes;
@@ -193,7 +288,7 @@ __device__ __forceinline__ TaskGeom task_geom(const AlignBatch &b, int t) {
 // ---------------------------------------------------------------------------------------------
 // Pass 1: score scan.  Single-warp CTAs pull tasks (longest first) from a global queue.
 // ---------------------------------------------------------------------------------------------
-template <int K, int S>
+template <int K, int S, bool LIN>
 __global__ void __launch_bounds__(32) align_scan_kernel(AlignBatch b, AlignGroup grp) {
     constexpr int R = K * S;
     const int lane = threadIdx.x;
@@ -204,21 +299,28 @@ __global__ void __launch_bounds__(32) align_scan_kernel(AlignBatch b, AlignGroup
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= grp.n_tasks) break;
         const TaskGeom g = task_geom<K, S>(b, grp.order[q]);
-        float Sv[R], Hv[R];
+        float Sv[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = lane * R + r + 1;
             Sv[r] = i <= g.L ? g.col0[i] : 0.f;
-            Hv[r] = INF;
         }
         const float diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
         float best = INF;
         int bestj = -1;
         if (lane == g.lastlane && g.col0[g.L] > INF) { best = g.col0[g.L]; bestj = 0; }
         float *ck = b.ckpt + b.ckpt_off[g.t];
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        Sweep<K, S, false>::run(g.codes, g.N, g.lut, 0, g.N, lane, g.nl, b.p, Sv, Hv, diag0, g.lastlane, g.kL, best,
-                                bestj, ck, ck + b.ckpt_rows, b.ckpt_rows, nullptr, -1, d0, d1, d2);
+        if (LIN) {
+            LinSweep<K, S>::run(g.codes, g.N, g.lut, lane, g.nl, b.p, Sv, diag0, g.lastlane, g.kL, best, bestj, ck,
+                                ck + b.ckpt_rows, b.ckpt_rows);
+        } else {
+            float Hv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) Hv[r] = INF;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            Sweep<K, S, false>::run(g.codes, g.N, g.lut, 0, g.N, lane, g.nl, b.p, Sv, Hv, diag0, g.lastlane, g.kL,
+                                    best, bestj, ck, ck + b.ckpt_rows, b.ckpt_rows, nullptr, -1, d0, d1, d2);
+        }
         if (lane == g.lastlane) {
             b.res[g.t].score = best;
             b.res[g.t].best_j = bestj;
@@ -392,9 +494,13 @@ __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGrou
 
 template <int K, int S>
 int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
-    int grid = ctx->num_sms * ALIGN_WARPS_PER_SM;
+    const bool lin = align_params_linear(b.p);
+    int grid = ctx->num_sms * (lin ? ALIGN_WARPS_PER_SM_LINEAR : ALIGN_WARPS_PER_SM);
     if (grid > g.n_tasks) grid = g.n_tasks;
-    align_scan_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
+    if (lin)
+        align_scan_kernel<K, S, true><<<grid, 32, 0, ctx->stream>>>(b, g);
+    else
+        align_scan_kernel<K, S, false><<<grid, 32, 0, ctx->stream>>>(b, g);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return STRIQUE_OK;
@@ -416,6 +522,14 @@ int launch_trace_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, i
 // sampling (scripts/STRique.py:507-513 'samples'); S = 1 serves arbitrary flank vectors.
 #define STRIQUE_ALIGN_INSTANCES(X) \
     X(2, 6) X(3, 6) X(4, 6) X(5, 6) X(6, 6) X(7, 6) X(8, 6) X(9, 6) X(10, 6) X(4, 1) X(8, 1) X(16, 1) X(32, 1)
+
+// linear gap costs: the scan may use LinSweep (see there for the exactness argument)
+bool align_params_linear(const strique_align_params &p) {
+    if (getenv("STRIQUE_NO_LINEAR_SCAN")) return false;
+    return p.gap_open_h == p.gap_extension_h && p.gap_open_v == p.gap_extension_v &&
+           fabsf(p.gap_extension_h) >= 1e-20f && fabsf(p.gap_extension_v) >= 1e-20f &&
+           fabsf(p.gap_extension_h) < 1e30f && fabsf(p.gap_extension_v) < 1e30f;
+}
 
 bool align_pick_kernel(int nlev, int samples, int *K, int *S) {
     if (samples == 6) {

@@ -24,6 +24,7 @@ namespace strique {
 
 constexpr int ALIGN_CKPT = 512;          // columns between DP-column checkpoints
 constexpr int ALIGN_WARPS_PER_SM = 8;    // resident single-warp CTAs per SM for the scan
+constexpr int ALIGN_WARPS_PER_SM_LINEAR = 16;   // ... for the linear-gap scan (half the registers)
 
 struct AlignGroup {        // tasks sharing one (K, S) kernel instantiation
     int K, S;
@@ -84,5 +85,6 @@ int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t 
 int align_launch_scan(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g);
 int align_launch_trace(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, int n_warps);
 bool align_pick_kernel(int nlev, int samples, int *K, int *S);
+bool align_params_linear(const strique_align_params &p);
 
 }  // namespace strique

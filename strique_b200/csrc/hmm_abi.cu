@@ -1,6 +1,7 @@
 // Host side of boundary #2: packing a compiled HMM into its device image, batch planning of the
 // Viterbi stage and the C ABI entry points strique_hmm_create / strique_viterbi_batch.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -137,66 +138,133 @@ int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out) {
     ctx->owned.push_back(dperm);
     m.blob = (const unsigned char *)dblob;
     m.perm = (const int32_t *)dperm;
-    return STRIQUE_OK;
+    return viterbi_fast_pack(ctx, d, out);
 }
 
-int viterbi_run_device(strique_ctx *ctx, const HmmModel &m, const double *x_dev, const int64_t *x_off_host, int n_seq,
-                       strique_viterbi_result *results_host, uint8_t *pattern_host, uint16_t *path_host) {
+// Decodes n_seq device-resident sequences, sequence s with model ctx->models[seq_model[s]].
+// Sequences whose model has a team-kernel image are decoded together per kernel shape (one launch
+// serves both strands / all loci); the rest go through the generic kernel model by model.
+int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
+                             int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,
+                             uint16_t *path_host) {
     if (n_seq == 0) return STRIQUE_OK;
     const int64_t total = x_off_host[n_seq];
-    for (int s = 0; s < n_seq; ++s)
+    const int n_models = (int)ctx->models.size();
+    for (int s = 0; s < n_seq; ++s) {
         if (x_off_host[s + 1] - x_off_host[s] >= (1ll << 30) || x_off_host[s + 1] < x_off_host[s])
             FAIL(ctx, STRIQUE_EINVAL, "viterbi: bad sequence offsets");
+        if (seq_model[s] < 0 || seq_model[s] >= n_models) FAIL(ctx, STRIQUE_EINVAL, "unknown HMM id");
+    }
     DevBuf &d_xoff = ctx->buf("vit.xoff"), &d_order = ctx->buf("vit.order"), &d_bpoff = ctx->buf("vit.bpoff"),
            &d_bp = ctx->buf("vit.bp"), &d_res = ctx->buf("vit.res"), &d_pat = ctx->buf("vit.pattern"),
-           &d_path = ctx->buf("vit.path"), &d_queue = ctx->buf("vit.queue");
+           &d_path = ctx->buf("vit.path"), &d_queue = ctx->buf("vit.queue"), &d_tasks = ctx->buf("vit.tasks"),
+           &d_models = ctx->buf("vit.models");
     TRY(d_xoff.ensure(ctx, (size_t)(n_seq + 1) * 8));
     TRY(d_res.ensure(ctx, (size_t)n_seq * sizeof(VitResult)));
     TRY(d_pat.ensure(ctx, std::max<int64_t>(total, 16)));
     if (path_host) TRY(d_path.ensure(ctx, std::max<int64_t>(total, 16) * 2));
     TRY(d_queue.ensure(ctx, 64));
+    TRY(d_bpoff.ensure(ctx, (size_t)n_seq * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_xoff.p, x_off_host, (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    // longest first, chunked so the back-pointer area (256 B per time step) fits the budget
-    std::vector<int32_t> order(n_seq);
-    std::iota(order.begin(), order.end(), 0);
     auto len = [&](int s) { return x_off_host[s + 1] - x_off_host[s]; };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len(a) > len(b); });
+    const bool force_generic = getenv("STRIQUE_VITERBI_GENERIC") != nullptr;
+    // ---- groups: one per team-kernel shape, one per model for the generic kernel -----------------------
+    struct Group { bool fast; VitFastShape shape; int model; std::vector<int32_t> ids; };
+    std::vector<Group> groups;
+    for (int s = 0; s < n_seq; ++s) {
+        const HmmModel &m = *ctx->models[seq_model[s]];
+        const bool fast = m.shape.wps > 0 && !force_generic;
+        Group *g = nullptr;
+        for (Group &c : groups)
+            if (c.fast == fast && (fast ? c.shape == m.shape : c.model == seq_model[s])) { g = &c; break; }
+        if (!g) { groups.push_back(Group{fast, m.shape, seq_model[s], {}}); g = &groups.back(); }
+        g->ids.push_back(s);
+        ctx->last_viterbi_edges += len(s) * m.n_edges;
+    }
+    std::vector<VitFastModelDev> fast_models(n_models);
+    for (int i = 0; i < n_models; ++i) fast_models[i] = ctx->models[i]->fast;
+    TRY(d_models.ensure(ctx, (size_t)n_models * sizeof(VitFastModelDev)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_models.p, fast_models.data(), (size_t)n_models * sizeof(VitFastModelDev), cudaMemcpyHostToDevice, ctx->stream));
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const int64_t budget_words = (int64_t)(std::max<size_t>((size_t)2 << 30, (size_t)((free_b + d_bp.cap) * 0.7)) / 8);
+    const int64_t budget_bytes = (int64_t)std::max<size_t>((size_t)2 << 30, (size_t)((free_b + d_bp.cap) * 0.7));
     std::vector<int64_t> bpoff(n_seq, 0);
-    int i0 = 0;
-    while (i0 < n_seq) {
-        int i1 = i0;
-        int64_t words = 0;
-        while (i1 < n_seq) {
-            const int64_t w = (len(order[i1]) + 1) * 32;
-            if (i1 > i0 && words + w > budget_words) break;
-            bpoff[order[i1]] = words;
-            words += w;
-            ++i1;
+    for (Group &g : groups) {
+        std::stable_sort(g.ids.begin(), g.ids.end(), [&](int a, int b) { return len(a) > len(b); });
+        const int64_t unit = g.fast ? 4 : 8;                               // bytes per back-pointer word
+        const int64_t words_per_step = g.fast ? g.shape.wps * 32 : 32;
+        size_t i0 = 0;
+        while (i0 < g.ids.size()) {
+            size_t i1 = i0;
+            int64_t words = 0;
+            while (i1 < g.ids.size()) {
+                const int64_t wds = (len(g.ids[i1]) + 1) * words_per_step;
+                if (i1 > i0 && (words + wds) * unit > budget_bytes) break;
+                bpoff[g.ids[i1]] = words;
+                words += wds;
+                ++i1;
+            }
+            const int n = (int)(i1 - i0);
+            TRY(d_bp.ensure(ctx, (size_t)words * unit));
+            TRY(d_order.ensure(ctx, (size_t)n * 4));
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_bpoff.p, bpoff.data(), (size_t)n_seq * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
+            if (!g.fast) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+                VitBatch b;
+                b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.n_seq = n; b.order = d_order.as<int32_t>();
+                b.bp = d_bp.as<unsigned long long>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
+                b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
+                b.queue = d_queue.as<int>();
+                TRY(viterbi_launch(ctx, *ctx->models[g.model], b));
+            } else {
+                // CTA tasks: per model, runs of `teams` consecutive (length-sorted) sequences; longest task first
+                const int teams = viterbi_fast_teams(g.shape);
+                std::vector<std::vector<int32_t>> per_model(n_models);
+                for (size_t i = i0; i < i1; ++i) per_model[seq_model[g.ids[i]]].push_back(g.ids[i]);
+                struct HostTask { int model; std::vector<int32_t> ids; int64_t maxlen; };
+                std::vector<HostTask> tasks;
+                int blob_cap = 0;
+                for (int mi = 0; mi < n_models; ++mi) {
+                    const auto &v = per_model[mi];
+                    if (v.empty()) continue;
+                    blob_cap = std::max(blob_cap, (int)align_up(ctx->models[mi]->fast.blob_bytes, 16));
+                    for (size_t k = 0; k < v.size(); k += teams) {
+                        HostTask t;
+                        t.model = mi;
+                        t.ids.assign(v.begin() + k, v.begin() + std::min(v.size(), k + teams));
+                        t.maxlen = len(t.ids[0]);
+                        tasks.push_back(std::move(t));
+                    }
+                }
+                std::stable_sort(tasks.begin(), tasks.end(), [](const HostTask &a, const HostTask &b) { return a.maxlen > b.maxlen; });
+                std::vector<int32_t> order;
+                std::vector<VitCtaTask> ctas;
+                for (const HostTask &t : tasks) {
+                    ctas.push_back(VitCtaTask{t.model, (int32_t)order.size(), (int32_t)t.ids.size()});
+                    order.insert(order.end(), t.ids.begin(), t.ids.end());
+                }
+                TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
+                VitFastBatch b;
+                b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
+                b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size();
+                b.models = d_models.as<VitFastModelDev>(); b.blob_cap = blob_cap;
+                b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
+                b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
+                b.queue = d_queue.as<int>();
+                TRY(viterbi_fast_launch(ctx, g.shape, b));
+            }
+            // host vectors above are read by the async copies: drain before they go out of scope
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            i0 = i1;
         }
-        const int n = i1 - i0;
-        TRY(d_bp.ensure(ctx, (size_t)words * 8));
-        TRY(d_order.ensure(ctx, (size_t)n * 4));
-        TRY(d_bpoff.ensure(ctx, (size_t)n_seq * 8));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_bpoff.p, bpoff.data(), (size_t)n_seq * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
-        VitBatch b;
-        b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.n_seq = n; b.order = d_order.as<int32_t>();
-        b.bp = d_bp.as<unsigned long long>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
-        b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
-        b.queue = d_queue.as<int>();
-        TRY(viterbi_launch(ctx, m, b));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        i0 = i1;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(results_host, d_res.p, (size_t)n_seq * sizeof(VitResult), cudaMemcpyDeviceToHost, ctx->stream));
     if (pattern_host) CUDA_TRY(ctx, cudaMemcpyAsync(pattern_host, d_pat.p, total, cudaMemcpyDeviceToHost, ctx->stream));
     if (path_host) CUDA_TRY(ctx, cudaMemcpyAsync(path_host, d_path.p, total * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->last_viterbi_edges += (total - x_off_host[0]) * m.n_edges;
     return STRIQUE_OK;
 }
 
@@ -215,6 +283,12 @@ extern "C" int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc
     return STRIQUE_OK;
 }
 
+extern "C" int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id) {
+    if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size()) return -1;
+    const VitFastShape &s = ctx->models[model_id]->shape;
+    return s.wps * 1000 + s.nh * 100 + s.nl * 10 + s.qc;
+}
+
 extern "C" int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_seq, const double *x,
                                      const int64_t *x_offsets, int memspace, strique_viterbi_result *results,
                                      uint8_t *pattern_out, uint16_t *path_out) {
@@ -231,5 +305,6 @@ extern "C" int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_s
         xd = d_x.as<double>();
     }
     ctx->last_viterbi_edges = 0;
-    return viterbi_run_device(ctx, *ctx->models[model_id], xd, x_offsets, n_seq, results, pattern_out, path_out);
+    std::vector<int32_t> seq_model(n_seq, model_id);
+    return viterbi_run_device_multi(ctx, seq_model.data(), xd, x_offsets, n_seq, results, pattern_out, path_out);
 }

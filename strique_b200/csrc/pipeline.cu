@@ -214,15 +214,12 @@ extern "C" int strique_detect_batch(strique_ctx *ctx, const strique_detect_confi
         vres.resize(n);
         // all groups write their patterns at absolute x offsets: size the shared buffer once
         TRY(ctx->buf("vit.pattern").ensure(ctx, std::max<int64_t>(16, xoff_all.back())));
-        for (int i = 0; i < n;) {
-            int k = i;
-            while (k < n && model_of(ord[k]) == model_of(ord[i])) ++k;
-            const int mid = model_of(ord[i]);
-            if (mid < 0 || mid >= (int)ctx->models.size()) FAIL(ctx, STRIQUE_EINVAL, "target without the requested HMM");
-            std::vector<int64_t> xo(xoff_all.begin() + i, xoff_all.begin() + k + 1);   // absolute offsets into x
-            TRY(viterbi_run_device(ctx, *ctx->models[mid], d_x.as<double>(), xo.data(), k - i, vres.data() + i, nullptr, nullptr));
-            i = k;
+        std::vector<int32_t> seq_model(n);
+        for (int i = 0; i < n; ++i) {
+            seq_model[i] = model_of(ord[i]);
+            if (seq_model[i] < 0 || seq_model[i] >= (int)ctx->models.size()) FAIL(ctx, STRIQUE_EINVAL, "target without the requested HMM");
         }
+        TRY(viterbi_run_device_multi(ctx, seq_model.data(), d_x.as<double>(), xoff_all.data(), n, vres.data(), nullptr, nullptr));
         stage_mark(ctx, 2 * stage + 1);
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         stage_collect(ctx, stage);

@@ -23,6 +23,8 @@ namespace strique {
 constexpr int VIT_WARPS = 8;          // warps (= sequences in flight) per CTA
 constexpr int VIT_MAX_SLOTS = 12;     // emitting slots + chain slots per lane (4 bits each, <= 48 bits)
 
+typedef strique_viterbi_result VitResult;
+
 enum { HMM_FLAG_COUNT = 1, HMM_FLAG_REPEAT = 2, HMM_FLAG_SEP = 4, HMM_FLAG_MOD = 8 };
 
 // Device view of a compiled model: a packed image (copied to shared memory by every CTA) plus
@@ -39,12 +41,50 @@ struct VitModelDev {
     const int32_t *perm;           // device position -> caller's emitting state id
 };
 
+// Device view of a model packed for the team kernel (viterbi_fast.cu): WPS warps per sequence, per
+// warp NH slots of <= 6 in-edges, NL slots of <= 3 in-edges and QC chain states per lane.  Value
+// column positions: emitting (w * (NH+NL) + slot) * 32 + lane, chain CB + (w * 32 + lane) * QC + q,
+// then START, then NEG.  All blob arrays are lane-minor ([...][32]).
+struct VitFastModelDev {
+    const unsigned char *blob;
+    int blob_bytes;
+    int off_w, off_src, off_em, off_flags, off_predw, off_cw, off_csrc, off_end_w, off_end_src;
+    int n_end, C;
+    const int32_t *perm;           // value position -> caller's emitting state id
+};
+
+struct VitFastShape {              // which instantiation of the team kernel serves the model (wps == 0: none)
+    int wps = 0, nh = 0, nl = 0, qc = 0;
+    bool operator==(const VitFastShape &o) const { return wps == o.wps && nh == o.nh && nl == o.nl && qc == o.qc; }
+};
+
 struct HmmModel {                 // host-side handle; device arrays owned by the context
     VitModelDev dev;
     int64_t n_edges = 0;          // in-edges of emitting + chain states (work unit of the Viterbi stage)
+    VitFastShape shape;
+    VitFastModelDev fast;
 };
 
-typedef strique_viterbi_result VitResult;
+struct VitCtaTask {                // <= 8/WPS sequences of one model, consecutive in `order`
+    int32_t model, first, count;
+};
+
+struct VitFastBatch {
+    const double *x;
+    const int64_t *x_off;
+    const int32_t *order;
+    const VitCtaTask *tasks;
+    int n_tasks;
+    const VitFastModelDev *models; // device array indexed by VitCtaTask::model
+    int blob_cap;                  // shared-memory bytes reserved for the model blob (multiple of 16)
+    uint32_t *bp;
+    const int64_t *bp_off;         // [n_seq] offset in 32-bit words (per sequence: (T+1) * WPS * 32 words)
+    VitResult *res;
+    uint8_t *pattern;
+    uint16_t *path;
+    int *queue;
+};
+
 
 struct VitBatch {
     const double *x;            // normalised samples, all sequences concatenated
@@ -60,10 +100,15 @@ struct VitBatch {
 };
 
 int viterbi_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
+// team kernel: packs the model if one of the instantiated shapes fits (sets m->shape), launch
+int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
+int viterbi_fast_launch(strique_ctx *ctx, const VitFastShape &shape, const VitFastBatch &b);
+int viterbi_fast_teams(const VitFastShape &shape);   // sequences per CTA task
+// decodes sequences of several models in one pass: seq_model[s] indexes ctx->models
+int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
+                             int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,
+                             uint16_t *path_host);
 int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out);
-// decodes n_seq sequences whose samples are device resident (x_dev) -> host results
-int viterbi_run_device(strique_ctx *ctx, const HmmModel &m, const double *x_dev, const int64_t *x_off_host, int n_seq,
-                       strique_viterbi_result *results_host, uint8_t *pattern_host, uint16_t *path_host);
 
 // x[t] = clip(clip(((src[t] - c1) / c2) * c3 + c4, lo, hi), lo2, hi2) for each segment
 struct PrepSeg {

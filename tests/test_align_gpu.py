@@ -106,3 +106,48 @@ def test_long_signal_score_only_property(ctx):
     assert np.float32(res['score'][0]) == np.float32(s0)
     assert res['best_j'][0] == bj
     assert abs(res['begin0'][0] - start) <= 8 and abs(res['end0'][0] - (start + len(planted))) <= 8
+
+
+def test_linear_gap_scan_equals_affine_scan_and_oracle(ctx, monkeypatch):
+    """gap_open == gap_extension selects the 3-FADD linear-gap scan (csrc/align.cu LinSweep); it must be
+    bit-identical to the general affine scan (forced with STRIQUE_NO_LINEAR_SCAN) and to the oracle,
+    including a second linear parameter set, column-1 effects (flank matching at the signal start)
+    and reads long enough to cross many checkpoint columns."""
+    c = rp.CAligner()
+    rng = np.random.default_rng(21)
+    for ps in [ac.PARAM_SETS[0], (-3.0, -7.0, -3.0, -7.0, 10.0, -2.0), (-0.25, -0.5, -0.25, -0.5, 4.0, 0.0)]:
+        _set(c, ps)
+        al = sa.align_raw(ctx)
+        _set(al, ps)
+        cs = [(a, b) for _, a, b in ac.cases(seed=123, n=120, max_L=150, max_N=1300)]
+        # flank planted at the very beginning of the signal: exercises H of DP column 0 (SeqAn's denormal infinity)
+        for _ in range(10):
+            lev = np.round(rng.uniform(60, 120, 20))
+            b = np.repeat(lev, 6)
+            a = np.concatenate([np.repeat(lev, rng.integers(5, 9, 20)), np.round(rng.uniform(60, 120, 300))])
+            cs.append((a[int(rng.integers(0, 4)):], b))
+        monkeypatch.delenv('STRIQUE_NO_LINEAR_SCAN', raising=False)
+        fast = al.align_overlap_batch(cs)
+        monkeypatch.setenv('STRIQUE_NO_LINEAR_SCAN', '1')
+        slow = al.align_overlap_batch(cs)
+        monkeypatch.delenv('STRIQUE_NO_LINEAR_SCAN', raising=False)
+        for (a, b), f, s in zip(cs, fast, slow):
+            s0, a0, b0 = c.align_overlap(a, b)
+            assert np.float32(f[0]) == np.float32(s[0]) == np.float32(s0)
+            assert np.array_equal(f[1], s[1]) and np.array_equal(f[1], a0)
+            assert np.array_equal(f[2], s[2]) and np.array_equal(f[2], b0)
+    # full-size property: 64 reads of ~60 k samples x 870 flank samples, every result field equal
+    ps = ac.PARAM_SETS[0]
+    n_sig, N, nlev = 32, 60000, 145
+    codes = np.repeat(rng.integers(60, 200, size=(n_sig * N) // 6 + 8).astype(np.uint8),
+                      rng.integers(6, 10, size=(n_sig * N) // 6 + 8))[:n_sig * N]
+    off = np.arange(n_sig + 1, dtype=np.int64) * N
+    vals = np.tile(np.linspace(50, 132, 256, dtype=np.float32), (n_sig, 1))
+    levels = rng.uniform(60, 120, 2 * nlev).astype(np.float32)
+    ts, tf = np.repeat(np.arange(n_sig), 2), np.tile([0, 1], n_sig)
+    args = (ps, codes, off, vals, levels, [0, nlev, 2 * nlev], 6, ts, tf, np.full(len(ts), 600), np.zeros_like(ts))
+    fast = ctx.align_batch(*args)
+    monkeypatch.setenv('STRIQUE_NO_LINEAR_SCAN', '1')
+    slow = ctx.align_batch(*args)
+    monkeypatch.delenv('STRIQUE_NO_LINEAR_SCAN', raising=False)
+    assert fast.tobytes() == slow.tobytes()
