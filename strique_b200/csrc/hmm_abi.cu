@@ -80,14 +80,21 @@ int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out) {
             continue;
         }
         const int l = perm[p];
+        // candidate order = the team kernel's (viterbi_fast.cu): the self loop, then the other edges
+        // from emitting states / START, then the edges from chain states (stable within each class)
         int k = 0;
-        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e, ++k) {
-            const int v = vpos(d->in_src[e]);
-            if (v < 0) FAIL(ctx, STRIQUE_EINVAL, "hmm: in-edge source out of range");
-            edge_w[(m.row_base[s] + k) * 32 + lane] = d->in_logw[e];
-            edge_src[(m.row_base[s] + k) * 32 + lane] = (uint16_t)v;
-            ++n_edges;
-        }
+        for (int pass = 0; pass < 3; ++pass)
+            for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) {
+                const bool from_chain = d->in_src[e] >= E && d->in_src[e] < E + C;
+                const int cls = from_chain ? 2 : (d->in_src[e] == l ? 0 : 1);
+                if (cls != pass) continue;
+                const int v = vpos(d->in_src[e]);
+                if (v < 0) FAIL(ctx, STRIQUE_EINVAL, "hmm: in-edge source out of range");
+                edge_w[(m.row_base[s] + k) * 32 + lane] = d->in_logw[e];
+                edge_src[(m.row_base[s] + k) * 32 + lane] = (uint16_t)v;
+                ++n_edges;
+                ++k;
+            }
         flags[p] = d->emit_flags ? d->emit_flags[l] : 0;
         const double a = d->emit_a[l], b = d->emit_b[l];
         if (d->emit_kind[l] == 0) {

@@ -48,7 +48,7 @@ struct VitModelDev {
 struct VitFastModelDev {
     const unsigned char *blob;
     int blob_bytes;
-    int off_w, off_src, off_em, off_flags, off_predw, off_cw, off_csrc, off_end_w, off_end_src;
+    int off_w, off_src, off_em, off_flags, off_predw, off_cw, off_wr, off_csrc, off_end_w, off_end_src;
     int n_end, C;
     const int32_t *perm;           // value position -> caller's emitting state id
 };

@@ -31,6 +31,14 @@ namespace {
 
 __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000ll); }
 
+// shared-memory gather from an absolute 32-bit shared address; the column parity is a compile-time
+// offset, so the load is one LDS.64 [R + IMM].  A plain (compiler-visible) load: it may be hoisted
+// and interleaved inside a phase but never across the barriers.
+template <int IMM>
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    return *reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)(addr + IMM)));
+}
+
 template <int WPS>
 __device__ __forceinline__ void team_sync(int id) {
     if (WPS > 1)
@@ -52,6 +60,10 @@ struct FastShape {
     static constexpr int STAGE_ROWS = 32;
     static constexpr int TEAM_DOUBLES = 2 * NVP;
     static constexpr int TEAM_STAGE_WORDS = STAGE_ROWS * WPS * 32;
+    // back-pointer word of a lane: one bit per "candidate beat the running best" comparison
+    //   high slot k: 5 bits at 5k; low slot k: 2 bits at 5 NH + 2 (k - NH); chain state q: 3 bits at CBIT + 3q
+    static constexpr int CBIT = 5 * NH + 2 * NL;
+    __host__ __device__ static constexpr int bit0(int k) { return k < NH ? 5 * k : 5 * NH + 2 * (k - NH); }
     __host__ __device__ static constexpr int row0(int k) { return k < NH ? 6 * k : 6 * NH + 3 * (k - NH); }
     __host__ __device__ static constexpr int deg(int k) { return k < NH ? 6 : 3; }
     static size_t smem_bytes(int blob_cap) {     // dynamic part: model blob + staged back-pointer rows
@@ -76,7 +88,8 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
     // dynamic shared layout: [model blob] [per team: staged back-pointer rows]
     unsigned char *blob = smem;
     double *vteam = vcols + (size_t)team * SH::TEAM_DOUBLES;
-    const uint32_t team_off = (uint32_t)team * SH::TEAM_DOUBLES * 8u;
+    // absolute shared address of this team's column 0 (static shared: < 64 KB, fits the 16-bit fields)
+    const uint32_t team_off = (uint32_t)__cvta_generic_to_shared(vteam);
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem + b.blob_cap) + (size_t)team * SH::TEAM_STAGE_WORDS;
 
     // per-lane model constants (registers)
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
     double em0[NSW], em1[NSW], em2[NSW];
     uint32_t kindmask = 0;
     uint32_t csrc[QCA];                   // two 16-bit byte offsets (entry edge 0, entry edge 1)
-    const double *cpw_s = nullptr, *cew_s = nullptr;   // chain weights stay in the shared model image
+    const double *cpw_s = nullptr, *cew_s = nullptr, *cwr_s = nullptr;   // chain weights stay in the shared model image
     int cur_model = -1;
     const int bar_id = 1 + team;
 
@@ -129,6 +142,7 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
                 const uint16_t *bcs = reinterpret_cast<const uint16_t *>(blob + m.off_csrc);
                 cpw_s = bpw + (size_t)w * QC * 32 + lane;
                 cew_s = bc + (size_t)w * QC * 2 * 32 + lane;
+                cwr_s = reinterpret_cast<const double *>(blob + m.off_wr) + (size_t)w * 5 * 32 + lane;
 #pragma unroll
                 for (int q = 0; q < QC; ++q) {
                     csrc[q] = ((uint32_t)bcs[((w * QC + q) * 2 + 0) * 32 + lane] * 8u + team_off) |
@@ -145,50 +159,85 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
         uint32_t *bp = b.bp + b.bp_off[seq];
 
         // silent chain states of column PAR: v[c] = max(entry edges from v, v[c-1] + w); returns nibbles
-        auto chain_phase = [&](auto par) -> uint32_t {
+        // E1 of one slot for the upcoming step (see the forward pass): reads column PS
+        double part[NSW];                                     // best E1 candidate of the upcoming step
+        double vprev[NSW];                                    // this lane's emitting values of the last column
+        uint32_t pbits = 0u;                                  // comparison bits of E1
+        auto e1_slot = [&](auto par_src, auto slot) {
+            constexpr int PS = decltype(par_src)::value;
+            constexpr int k = decltype(slot)::value;
+            // row 0 of a slot is the state's self loop: its value is still in this lane's register
+            double best = vprev[k] + wreg[SH::row0(k)];
+#pragma unroll
+            for (int d = 1; d < SH::deg(k) - 1; ++d) {
+                const int r = SH::row0(k) + d;
+                const uint32_t addr = (r & 1) ? (srcreg[r / 2] >> 16) : (srcreg[r / 2] & 0xffffu);
+                const double cand = lds_f64<PS * NVP * 8>(addr) + wreg[r];
+                if (cand > best) {                            // bit d-1: candidate d beat the running best
+                    best = cand;
+                    pbits |= 1u << (SH::bit0(k) + d - 1);
+                }
+            }
+            part[k] = best;
+        };
+        // Silent chain states of column PAR: v[c] = max(entry edges from v, v[c-1] + w), a max-plus scan
+        // (Kogge-Stone over the lanes; the summed hop weights of every round are model constants, cwr,
+        // -inf for the lanes a round does not reach).  When WITH_E1, the E1 work of the next step is
+        // issued between the scan rounds: both only read the emitting values of column PAR, and the
+        // independent compare chains fill the shuffle / fp64 latencies of the scan.
+        auto chain_phase = [&](auto par, auto with_e1) -> uint32_t {
             constexpr int PAR = decltype(par)::value;
-            if (QC == 0) return 0u;
+            constexpr bool WITH_E1 = decltype(with_e1)::value;
+            typedef std::integral_constant<int, PAR> P;
+            if (WITH_E1) pbits = 0u;
+            if (QC == 0) {
+                if (WITH_E1) {
+                    e1_slot(P(), std::integral_constant<int, 0>());
+                    if (NSW > 1) e1_slot(P(), std::integral_constant<int, (NSW > 1 ? 1 : 0)>());
+                    if (NSW > 2) e1_slot(P(), std::integral_constant<int, (NSW > 2 ? 2 : 0)>());
+                    if (NSW > 3) e1_slot(P(), std::integral_constant<int, (NSW > 3 ? 3 : 0)>());
+                }
+                return 0u;
+            }
             double a[QCA], cpw[QCA];
-            int ka[QCA];
-            double A = NINF, W = 0.0;
-            const unsigned char *vb = reinterpret_cast<const unsigned char *>(vcols) + PAR * NVP * 8;
+            double A = NINF;
+            uint32_t bits = 0u;
             double *v = vteam + PAR * NVP;
 #pragma unroll
             for (int q = 0; q < QC; ++q) {
                 cpw[q] = cpw_s[q * 32];
-                const double c0 = *reinterpret_cast<const double *>(vb + (csrc[q] & 0xffffu)) + cew_s[(2 * q) * 32];
-                const double c1 = *reinterpret_cast<const double *>(vb + (csrc[q] >> 16)) + cew_s[(2 * q + 1) * 32];
-                double best = c0;          // c0 > -inf or best stays -inf either way
-                int k = c0 > NINF ? 1 : 0;
-                if (c1 > best) { best = c1; k = 2; }
+                const double c0 = lds_f64<PAR * NVP * 8>(csrc[q] & 0xffffu) + cew_s[(2 * q) * 32];
+                const double c1 = lds_f64<PAR * NVP * 8>(csrc[q] >> 16) + cew_s[(2 * q + 1) * 32];
+                double best = c0;
+                if (c0 > NINF) bits |= 1u << (SH::CBIT + 3 * q);
+                if (c1 > best) { best = c1; bits |= 2u << (SH::CBIT + 3 * q); }
                 a[q] = best;
-                ka[q] = k;
                 const double t0 = A + cpw[q];
                 A = best >= t0 ? best : t0;
-                W += cpw[q];
             }
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double Al = __shfl_up_sync(0xffffffffu, A, off);
-                const double Wl = __shfl_up_sync(0xffffffffu, W, off);
-                if (lane >= off) {
-                    const double t0 = Al + W;
-                    A = A >= t0 ? A : t0;
-                    W = Wl + W;
-                }
-            }
+            auto round = [&](const int r) {
+                const double Al = __shfl_up_sync(0xffffffffu, A, 1 << r);
+                const double t0 = Al + cwr_s[r * 32];
+                A = A >= t0 ? A : t0;
+            };
+            round(0);
+            if (WITH_E1) e1_slot(P(), std::integral_constant<int, 0>());
+            round(1);
+            if (WITH_E1 && NSW > 1) e1_slot(P(), std::integral_constant<int, (NSW > 1 ? 1 : 0)>());
+            round(2);
+            if (WITH_E1 && NSW > 2) e1_slot(P(), std::integral_constant<int, (NSW > 2 ? 2 : 0)>());
+            round(3);
+            if (WITH_E1 && NSW > 3) e1_slot(P(), std::integral_constant<int, (NSW > 3 ? 3 : 0)>());
+            round(4);
             double D = __shfl_up_sync(0xffffffffu, A, 1);
             if (lane == 0) D = NINF;
-            uint32_t nib = 0u;
 #pragma unroll
             for (int q = 0; q < QC; ++q) {
                 const double t0 = D + cpw[q];
-                int arg;
-                if (a[q] >= t0) { D = a[q]; arg = ka[q]; } else { D = t0; arg = 0; }
+                if (a[q] >= t0) { D = a[q]; bits |= 4u << (SH::CBIT + 3 * q); } else { D = t0; }
                 v[CB + (w * 32 + lane) * QC + q] = D;
-                nib |= (uint32_t)arg << (4 * (NSW + q));
             }
-            return nib;
+            return bits;
         };
         typedef std::integral_constant<int, 0> Par0;
         typedef std::integral_constant<int, 1> Par1;
@@ -199,11 +248,19 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
         team_sync<WPS>(bar_id);
         if (w == 0 && lane == 0) buf0[P_START] = 0.0;
         team_sync<WPS>(bar_id);
-        bp[w * 32 + lane] = chain_phase(Par0());
+        bp[w * 32 + lane] = chain_phase(Par0(), std::false_type());
         team_sync<WPS>(bar_id);
 
-        // ---- forward pass (two steps per iteration: the column parity is a compile-time constant) ------
+        // ---- forward pass ----------------------------------------------------------------------------
+        // Software pipeline inside the warp: the in-edges of an emitting state are split into those whose
+        // source is an emitting state / START (rows 0..deg-2 of the slot, "E1") and the one whose source
+        // is a silent chain state (last row, "E2").  E1 of step t+1 only needs the emitting values of
+        // column t, so it runs in the same basic block as the delete-chain scan of column t and fills the
+        // shuffle / fp64 latencies of that scan; E2 + emission follow the barrier that publishes the chain.
+        // Two steps per loop iteration make the column parity a compile-time constant.
         double xr = lane < T ? x[lane] : 0.0, xn = 0.0;      // samples of the current / next 32-step block
+#pragma unroll
+        for (int k = 0; k < NSW; ++k) { part[k] = NINF; vprev[k] = NINF; }
         auto step = [&](const int t, auto par) {
             constexpr int PAR = decltype(par)::value;         // parity of the NEW column: t odd -> 1
             const int tl = (t - 1) & 31;
@@ -213,25 +270,22 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
             }
             const double xt = __shfl_sync(0xffffffffu, xr, tl);
             const bool xnan = xt != xt;
-            const unsigned char *vob = reinterpret_cast<const unsigned char *>(vcols) + (1 - PAR) * NVP * 8;
             double *vnew = vteam + PAR * NVP;
-            uint32_t word = 0u;
-            double nv[NSW];
+            uint32_t word = pbits;
+            // E2: the chain-source candidate (last row of the slot) against the best E1 candidate
+            double cc[NSW];
 #pragma unroll
             for (int k = 0; k < NSW; ++k) {
-                double best = NINF;
-                uint32_t arg = 0u;
+                const int r = SH::row0(k) + SH::deg(k) - 1;
+                const uint32_t addr = (r & 1) ? (srcreg[r / 2] >> 16) : (srcreg[r / 2] & 0xffffu);
+                cc[k] = lds_f64<(1 - PAR) * NVP * 8>(addr) + wreg[r];
+            }
 #pragma unroll
-                for (int d = 0; d < SH::deg(k); ++d) {
-                    const int r = SH::row0(k) + d;
-                    const uint32_t off = (r & 1) ? (srcreg[r / 2] >> 16) : (srcreg[r / 2] & 0xffffu);
-                    const double cand = *reinterpret_cast<const double *>(vob + off) + wreg[r];
-                    if (d == 0) {
-                        best = cand;                          // arg 0 also stands for "all candidates -inf"
-                    } else if (cand > best) {
-                        best = cand;
-                        arg = (uint32_t)d << (4 * k);
-                    }
+            for (int k = 0; k < NSW; ++k) {
+                double best = part[k];
+                if (cc[k] > best) {
+                    best = cc[k];
+                    word |= 1u << (SH::bit0(k) + SH::deg(k) - 2);
                 }
                 double e;
                 if ((kindmask >> k) & 1u) {
@@ -241,18 +295,23 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
                     e = em1[k] - (dx * dx) * em2[k];
                 }
                 if (xnan) e = 0.0;
-                nv[k] = best + e;
-                word |= arg;
+                vprev[k] = best + e;
             }
 #pragma unroll
-            for (int k = 0; k < NSW; ++k) vnew[(w * NSW + k) * 32 + lane] = nv[k];
+            for (int k = 0; k < NSW; ++k) vnew[(w * NSW + k) * 32 + lane] = vprev[k];
             team_sync<WPS>(bar_id);
             if (t == 1 && w == 0 && lane == 0) buf0[P_START] = NINF;    // START exists before the first sample only
-            word |= chain_phase(par);
+            word |= chain_phase(par, std::true_type());       // delete chains of column t + E1 of step t+1
             bp[(size_t)t * RW + w * 32 + lane] = word;
             if (tl == 31) xr = xn;
             team_sync<WPS>(bar_id);
         };
+        // E1 of step 1 from the initial column (its START entry is still 0)
+        pbits = 0u;
+        e1_slot(Par0(), std::integral_constant<int, 0>());
+        if (NSW > 1) e1_slot(Par0(), std::integral_constant<int, (NSW > 1 ? 1 : 0)>());
+        if (NSW > 2) e1_slot(Par0(), std::integral_constant<int, (NSW > 2 ? 2 : 0)>());
+        if (NSW > 3) e1_slot(Par0(), std::integral_constant<int, (NSW > 3 ? 3 : 0)>());
         {
             int t = 1;
             for (; t + 1 <= T; t += 2) {
@@ -334,14 +393,15 @@ __global__ void __launch_bounds__(256, 2) viterbi_team_kernel(VitFastBatch b) {
                     if (path && lane == 0) path[t - 1] = (uint16_t)m.perm[s];
                     const int ls = s & 31, slot = s >> 5, sw = slot / NSW, k = slot - sw * NSW;
                     const uint32_t wd = row[sw * 32 + ls];
-                    const int arg = (int)((wd >> (4 * k)) & 15u);
+                    const uint32_t mask = k < NH ? (wd >> (5 * k)) & 31u : (wd >> (5 * NH + 2 * (k - NH))) & 3u;
+                    const int arg = mask ? 32 - __clz(mask) : 0;          // the last candidate that beat the running best
                     const int r0 = k < NH ? 6 * k : 6 * NH + 3 * (k - NH);
                     s = src_tab[((size_t)sw * ROWS + r0 + arg) * 32 + ls];
                     --t;
                 } else {
                     const int c = s - CB, cw_ = c / (32 * QCA), lc = (c / QCA) & 31, q = c % QCA;
-                    const uint32_t wd = row[cw_ * 32 + lc];
-                    const int arg = (int)((wd >> (4 * (NSW + q))) & 15u);
+                    const uint32_t wd = (row[cw_ * 32 + lc] >> (SH::CBIT + 3 * q)) & 7u;
+                    const int arg = (wd & 4u) ? ((wd & 2u) ? 2 : (wd & 1u)) : 0;   // entry edge 1/2, or 0: previous chain state
                     if (arg == 0) s = s - 1; else s = csrc_tab[((size_t)(cw_ * QCA + q) * 2 + arg - 1) * 32 + lc];
                 }
             }
@@ -401,7 +461,11 @@ int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) 
     int n_hi = 0, max_deg = 0;
     for (int l = 0; l < E; ++l) {
         max_deg = std::max(max_deg, degree(l));
-        if (degree(l) > 3) ++n_hi;
+        int nc = 0;
+        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) nc += (d->in_src[e] >= E && d->in_src[e] < E + C) ? 1 : 0;
+        int nself = 0;
+        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) nself += d->in_src[e] == l ? 1 : 0;
+        if (degree(l) - nc - nself > 1) ++n_hi;                // needs a high slot (self + 4 gathers + chain row)
     }
     if (max_deg > 6 || d->n_end > 64) return STRIQUE_OK;
     // chains: maximal runs of chain states linked by finite predecessor weights
@@ -436,15 +500,28 @@ int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) 
     std::vector<std::pair<int, int>> hi_slots, lo_slots;
     for (int k = 0; k < NH; ++k) for (int w = 0; w < WPS; ++w) hi_slots.push_back({w, k});
     for (int k = NH; k < NSW; ++k) for (int w = 0; w < WPS; ++w) lo_slots.push_back({w, k});
-    // high slots take every state with more than 3 in-edges, then more states while the low slots
-    // would overflow; low slots take the rest
+    // A high slot has 5 rows for emitting / START sources + 1 row for a chain source, a low slot 2 + 1.
+    auto n_chain_src = [&](int l) {
+        int n = 0;
+        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) n += (d->in_src[e] >= E && d->in_src[e] < E + C) ? 1 : 0;
+        return n;
+    };
+    // gather rows needed besides the self loop (row 0) and the chain source (last row): <= 4 high, <= 1 low
+    auto n_other = [&](int l) {
+        int n = 0;
+        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e)
+            n += (d->in_src[e] != l && !(d->in_src[e] >= E && d->in_src[e] < E + C)) ? 1 : 0;
+        return n;
+    };
     std::vector<int32_t> hi_list, lo_list;
+    for (int l : byDeg) {
+        if (n_chain_src(l) > 1 || n_other(l) > 4) return STRIQUE_OK;   // does not fit the row template: generic kernel
+        if (n_other(l) > 1) hi_list.push_back(l);
+    }
     for (int l : byDeg)
-        if (degree(l) > 3) hi_list.push_back(l);
-    for (int l : byDeg)
-        if (degree(l) <= 3) {
+        if (n_other(l) <= 1) {
             if ((int)hi_list.size() < WPS * NH * 32 && E - (int)hi_list.size() > WPS * NL * 32)
-                hi_list.push_back(l);
+                hi_list.push_back(l);                          // only when the low slots would overflow
             else
                 lo_list.push_back(l);
         }
@@ -481,6 +558,7 @@ int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) 
     f.off_em = section((size_t)3 * CB * 8);
     f.off_predw = section((size_t)WPS * QCA * 32 * 8);
     f.off_cw = section((size_t)WPS * QCA * 2 * 32 * 8);
+    f.off_wr = section((size_t)WPS * 5 * 32 * 8);
     f.off_end_w = section((size_t)d->n_end * 8);
     f.off_src = section((size_t)WPS * ROWS * 32 * 2);
     f.off_csrc = section((size_t)WPS * QCA * 2 * 32 * 2);
@@ -505,16 +583,24 @@ int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) 
         const int slot = p / 32, lane = p % 32, w = slot / NSW, k = slot % NSW;
         const int l = state_at[p];
         if (l < 0) {   // padding state: uniform over an empty range, never reachable
-            bf[p] = 0x80; be[p] = 1.0; be[CB + p] = 0.0; be[2 * CB + p] = -INFINITY;
+            bf[p] = 0x80 | 0x40; be[p] = 1.0; be[CB + p] = 0.0; be[2 * CB + p] = -INFINITY;
             continue;
         }
         perm[p] = l;
-        int kk = 0;
-        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e, ++kk) {
+        // row 0: the self loop (weight -inf if the state has none; the kernel reads the value from its
+        // own register), rows 1..: other emitting / START sources, last row: the chain source
+        int kk = 1;
+        const int last_row = row0(k) + (k < NH ? 5 : 2);
+        bw[((size_t)w * ROWS + row0(k)) * 32 + lane] = -INFINITY;
+        bs[((size_t)w * ROWS + row0(k)) * 32 + lane] = (uint16_t)p;
+        for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) {
             const int v = vpos(d->in_src[e]);
             if (v < 0) FAIL(ctx, STRIQUE_EINVAL, "hmm: in-edge source out of range");
-            bw[((size_t)w * ROWS + row0(k) + kk) * 32 + lane] = d->in_logw[e];
-            bs[((size_t)w * ROWS + row0(k) + kk) * 32 + lane] = (uint16_t)v;
+            const bool from_chain = d->in_src[e] >= E && d->in_src[e] < E + C;
+            const int row = from_chain ? last_row : (d->in_src[e] == l ? row0(k) : row0(k) + kk++);
+            if (row >= last_row && !from_chain) FAIL(ctx, STRIQUE_EINVAL, "hmm: team-kernel row template overflow");
+            bw[((size_t)w * ROWS + row) * 32 + lane] = d->in_logw[e];
+            bs[((size_t)w * ROWS + row) * 32 + lane] = (uint16_t)v;
         }
         const uint8_t fl = d->emit_flags ? (d->emit_flags[l] & 0x7f) : 0;
         const double a = d->emit_a[l], b = d->emit_b[l];
@@ -540,6 +626,25 @@ int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) 
                 bcs[((w * QCA + q) * 2 + kk) * 32 + lane] = (uint16_t)vpos(src);
             }
         }
+    // summed hop weights seen by every round of the kernel's Kogge-Stone scan (same association as
+    // the shuffle recurrence W <- W(lane - off) + W), -inf where the round does not reach
+    double *bwr = (double *)(blob.data() + f.off_wr);
+    for (int w = 0; w < WPS; ++w) {
+        double W[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            W[lane] = 0.0;
+            for (int q = 0; q < QCA; ++q) W[lane] += bpw[(w * QCA + q) * 32 + lane];
+        }
+        for (int r = 0; r < 5; ++r) {
+            const int off_ = 1 << r;
+            double Wn[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                bwr[(w * 5 + r) * 32 + lane] = lane >= off_ ? W[lane] : -INFINITY;
+                Wn[lane] = lane >= off_ ? W[lane - off_] + W[lane] : W[lane];
+            }
+            memcpy(W, Wn, sizeof(W));
+        }
+    }
     for (int e = 0; e < d->n_end; ++e) {
         const int v = vpos(d->end_src[e]);
         if (v < 0 || v == P_START) FAIL(ctx, STRIQUE_EINVAL, "hmm: END edge source out of range");
