@@ -190,10 +190,9 @@ template <int K, int S>
 struct LinSweep {
     static constexpr int R = K * S;
 
-    template <bool FIRST, bool CK>
+    template <bool FIRST>
     __device__ __forceinline__ static float column(float (&Sv)[R], const float (&lutc)[K], float diag, float cS,
-                                                   const float gh, const float gv, float *__restrict__ ckS,
-                                                   float *__restrict__ ckH) {
+                                                   const float gh, const float gv) {
         const float INF = STRIQUE_SEQAN_INF;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -204,11 +203,15 @@ struct LinSweep {
             const float v = cS + gv;
             cS = fmax3(inter, h, v);
             Sv[r] = cS;
-            if (CK) { ckS[r] = cS; ckH[r] = h; }
         }
         return cS;
     }
 
+    // Loop structure: the first nl steps (where some lane is at DP column 1 and needs the FIRST
+    // variant) run a small general loop; the steady state has ONE straight-line column body (no code
+    // variants that would have to be merged with register moves), two steps per iteration so the
+    // score rows ping-pong between two register sets, checkpoint columns only add stores around the
+    // body, and the best-cell tracking is branch free.
     __device__ __forceinline__ static void run(const uint16_t *__restrict__ codes, const int N,
                                                const float *__restrict__ lut, const int lane, const int nl,
                                                const strique_align_params &p, float (&Sv)[R], float diag_next,
@@ -219,17 +222,28 @@ struct LinSweep {
         float lutc[K], lutn[K];
         float botS = 0.f;
         const int last_step = N + nl - 1;
+        const float *lut_lane = lut + lane * K;
         {
             const int c = codes[clampi(-lane, 0, N - 1)];
-            const float *row = lut + (size_t)c * row_len + lane * K;
+            const float *row = lut_lane + (size_t)c * row_len;
 #pragma unroll
             for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
         }
         int code_nx = codes[clampi(1 - lane, 0, N - 1)];
-        for (int s = 1; s <= last_step; ++s) {
-            const int j = s - lane;
+        auto track_best = [&](const int j) {
+            float last = Sv[S - 1];
+#pragma unroll
+            for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
+            const bool upd = lane == lastlane && last > best;      // strict >: first maximum wins (dp_scout.h:175)
+            best = upd ? last : best;
+            bestj = upd ? j : bestj;
+        };
+        // general step: any column (DP column 1, checkpoint columns, lanes outside [1, N]); used for the
+        // first nl steps and the last nl - 1, where the lanes are not all inside the signal
+        auto general = [&](const int st) {
+            const int j = st - lane;
             {
-                const float *row = lut + (size_t)code_nx * row_len + lane * K;
+                const float *row = lut_lane + (size_t)code_nx * row_len;
 #pragma unroll
                 for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k);
             }
@@ -237,27 +251,61 @@ struct LinSweep {
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);
             if (lane == 0) inS = 0.f;            // DP row 0: free begin, S = 0
             if (j > 0 && j <= N && lane < nl) {
+                const bool ck = (j & (ALIGN_CKPT - 1)) == 0;
+                const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
+                if (ck) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) ckH[o + r] = Sv[r] + gh;
+                }
                 const float diag = diag_next;
                 diag_next = inS;
-                if (j == 1) {
-                    botS = column<true, false>(Sv, lutc, diag, inS, gh, gv, nullptr, nullptr);
-                } else if ((j & (ALIGN_CKPT - 1)) == 0) {
-                    const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
-                    botS = column<false, true>(Sv, lutc, diag, inS, gh, gv, ckS + o, ckH + o);
-                } else {
-                    botS = column<false, false>(Sv, lutc, diag, inS, gh, gv, nullptr, nullptr);
-                }
-                if (lane == lastlane) {
-                    float last = Sv[S - 1];
+                if (j == 1) botS = column<true>(Sv, lutc, diag, inS, gh, gv);
+                else botS = column<false>(Sv, lutc, diag, inS, gh, gv);
+                if (ck) {
 #pragma unroll
-                    for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
-                    if (last > best) { best = last; bestj = j; }   // strict >: first maximum wins (dp_scout.h:175)
+                    for (int r = 0; r < R; ++r) ckS[o + r] = Sv[r];
                 }
+                track_best(j);
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) lutc[k] = lutn[k];
             code_nx = code_nx2;
+        };
+        // steady step: every lane is at a column 2 <= j <= N, so the column body runs unguarded (idle
+        // lanes >= nl compute on zeros); only the checkpoint stores are conditional
+        auto steady = [&](const int st, const float (&lc)[K], float (&ln)[K]) {
+            const int j = st - lane;
+            {
+                const float *row = lut_lane + (size_t)code_nx * row_len;
+#pragma unroll
+                for (int k = 0; k < K; ++k) ln[k] = __ldg(row + k);
+            }
+            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
+            float inS = __shfl_up_sync(0xffffffffu, botS, 1);
+            if (lane == 0) inS = 0.f;
+            const bool ck = (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
+            const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
+            if (ck) {                             // H of the checkpoint column: S of the previous column + g_h
+#pragma unroll
+                for (int r = 0; r < R; ++r) ckH[o + r] = Sv[r] + gh;
+            }
+            const float diag = diag_next;
+            diag_next = inS;
+            botS = column<false>(Sv, lc, diag, inS, gh, gv);
+            if (ck) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) ckS[o + r] = Sv[r];
+            }
+            track_best(j);
+            code_nx = code_nx2;
+        };
+        int s = 1;
+        for (; s <= nl && s <= last_step; ++s) general(s);
+        for (; s + 1 <= N; s += 2) {
+            steady(s, lutc, lutn);
+            steady(s + 1, lutn, lutc);
         }
+        for (; s <= last_step; ++s) general(s);
     }
 };
 
