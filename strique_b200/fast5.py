@@ -12,6 +12,7 @@ B-tree v1 / SNOD / local heap), compact new-style groups (link messages), chunke
 contiguous or compact datasets of fixed-point integers, deflate and shuffle filters.
 """
 import os
+import sys
 import re
 import struct
 import tarfile
@@ -154,6 +155,62 @@ class _MiniHDF5:
             addr = members[part]
         return addr
 
+    def attr_string(self, addr, name):
+        """String attribute `name` of the object at `addr` (attribute message 0x0C, versions 1-3;
+        fixed-length strings, or variable-length strings stored in a global heap collection)."""
+        for mtype, _, d in self._messages(addr):
+            if mtype != 0x0C:
+                continue
+            ver = d[0]
+            nlen, tsize, ssize = self._u_b(d, 2, 2), self._u_b(d, 4, 2), self._u_b(d, 6, 2)
+            p = 8 + (1 if ver == 3 else 0)
+            pad = (lambda n: (n + 7) // 8 * 8) if ver == 1 else (lambda n: n)
+            aname = d[p:p + nlen].split(b'\0')[0].decode('utf-8')
+            p += pad(nlen)
+            dtype = d[p:p + tsize]
+            p += pad(tsize) + pad(ssize)
+            if aname != name:
+                continue
+            cls = dtype[0] & 0x0f
+            if cls == 3:                                   # fixed-length string
+                size = self._u_b(dtype, 4, 4)
+                return d[p:p + size].split(b'\0')[0].decode('utf-8')
+            if cls == 9:                                   # variable length: (length, heap address, object index)
+                length, heap, idx = self._u_b(d, p, 4), self._u_b(d, p + 4, 8), self._u_b(d, p + 12, 4)
+                return self._global_heap_object(heap, idx)[:length].decode('utf-8')
+            raise HDF5Error('attribute {} is not a string'.format(name))
+        raise KeyError(name)
+
+    def _global_heap_object(self, heap_addr, index):
+        h = heap_addr + self.base
+        if self.buf[h:h + 4] != b'GCOL':
+            raise HDF5Error('bad global heap collection')
+        size = self._u(h + 8, 8)
+        p = h + 16
+        while p + 16 <= h + size:
+            idx, osize = self._u(p, 2), self._u(p + 8, 8)
+            if idx == index:
+                return self.buf[p + 16:p + 16 + osize]
+            if idx == 0:
+                break
+            p += 16 + (osize + 7) // 8 * 8
+        raise HDF5Error('global heap object not found')
+
+    def find_signal_path(self, raw_group_path):
+        """Like find_signal, but returns (address of the group holding the Signal dataset, dataset address)."""
+        def visit(addr):
+            for name, child in sorted(self.links(addr).items()):
+                if 'Signal' in name:
+                    return addr, child
+                try:
+                    sub = visit(child)
+                except HDF5Error:
+                    sub = None
+                if sub is not None:
+                    return sub
+            return None
+        return visit(self.resolve(raw_group_path))
+
     def find_signal(self, raw_group_path):
         """Depth-first search below `raw_group_path` for the first member whose path contains
         'Signal' (the reference uses h5py `visit`, fast5Index.py:80)."""
@@ -283,8 +340,71 @@ def read_raw_signal(f5_file, offset=''):
     return f.read_dataset(addr)
 
 
+def read_id_of(f5_file, offset=''):
+    """`read_id` attribute of the group holding the Signal dataset (fast5Index.py:62-74)."""
+    raw_group = '/'.join([x for x in (offset, 'Raw') if x])
+    if _h5py is not None:  # pragma: no cover - depends on the environment
+        with _h5py.File(f5_file, 'r') as fp:
+            s = fp[raw_group].visit(lambda name: name if 'Signal' in name else None)
+            rid = fp[raw_group + '/' + s.rpartition('/')[0]].attrs['read_id']
+            return rid.decode('utf-8') if isinstance(rid, bytes) else str(rid)
+    f = _MiniHDF5(f5_file)
+    found = f.find_signal_path(raw_group)
+    if found is None:
+        raise HDF5Error('no Signal dataset below ' + raw_group)
+    return f.attr_string(found[0], 'read_id')
+
+
+def top_level_groups(f5_file):
+    if _h5py is not None:  # pragma: no cover
+        with _h5py.File(f5_file, 'r') as fp:
+            return list(fp)
+    f = _MiniHDF5(f5_file)
+    return sorted(f.links(f.root))
+
+
 class fast5Index(object):
     """Index-file backed raw-signal lookup (fast5Index.py:45-56, 220-233)."""
+
+    @staticmethod
+    def index(input, recursive=False, output_prefix='', tmp_prefix=None):
+        """Yields `relative/path.fast5[/group]\tREAD_ID` records (fast5Index.py:132-179): single-read
+        files, multi-read ("bulk") files whose top-level groups are the reads, and tar archives of
+        single-read files."""
+        import glob
+        if tmp_prefix and not os.path.exists(tmp_prefix):
+            os.makedirs(tmp_prefix)
+        if os.path.isfile(input):
+            input_files = [input]
+        elif recursive:
+            input_files = [os.path.join(dp, f) for dp, _, files in os.walk(input) for f in files
+                           if f.endswith('.fast5') or f.endswith('.tar')]
+        else:
+            input_files = glob.glob(os.path.join(input, '*.fast5')) + glob.glob(os.path.join(input, '*.tar'))
+        start = input if os.path.isdir(input) else os.path.dirname(input)
+        for input_file in sorted(input_files):
+            rel = os.path.normpath(os.path.join(output_prefix, os.path.dirname(os.path.relpath(input_file, start=start)),
+                                                os.path.basename(input_file)))
+            if input_file.endswith('.tar'):
+                with tempfile.TemporaryDirectory(prefix=tmp_prefix) as tmp, tarfile.open(input_file) as tar:
+                    tar.extractall(path=tmp)
+                    for dp, _, files in os.walk(tmp):
+                        for f in sorted(files):
+                            if f.endswith('.fast5'):
+                                try:
+                                    rid = read_id_of(os.path.join(dp, f))
+                                except Exception:  # noqa: BLE001 - the reference skips unreadable members
+                                    print('[ERROR] Failed to open {f5}, skip file for indexing'.format(f5=f), file=sys.stderr)
+                                    continue
+                                yield '\t'.join([os.path.normpath(os.path.join(
+                                    rel, os.path.relpath(os.path.join(dp, f), start=tmp))), rid])
+                continue
+            groups = top_level_groups(input_file)
+            if 'Raw' in groups or 'UniqueGlobalKey' in groups:      # single-read layout
+                yield '\t'.join([rel, read_id_of(input_file)])
+            else:                                                    # multi-read: one group per read
+                for g in groups:
+                    yield '\t'.join([os.path.join(rel, g), read_id_of(input_file, offset=g)])
 
     def __init__(self, index_file=None, tmp_prefix=None):
         self.index_file = index_file
