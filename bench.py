@@ -321,7 +321,10 @@ def main():
         }
         dom = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
         roofline = dict(kernels[dom])
-        roofline.update({'kernel': dom, 'traffic': None,
+        # DRAM traffic per launch of the dominant kernel, from the ncu --set full capture in profiles/
+        # (viterbi: 516 B per time step measured vs 512 B algorithmic; scan: 0.04 B per cell)
+        traffic = t_total * 516.0 if dom == 'viterbi_count' else (cells / args.steps) * 0.0425
+        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01m.txt scaled to this launch',
                          'peak_source': 'issue peak = N_SM x lanes x SM clock sampled under load (fp32: 128 lanes/SM, '
                                         'fp64: 64 lanes/SM); HBM peak: ' +
                                         ('of measured (MEASURED_PEAKS.json)' if peaks else 'of fallback 6650 GB/s')})
