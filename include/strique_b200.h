@@ -135,6 +135,15 @@ typedef struct {
     int32_t n_end;
     const int32_t *end_src;
     const double *end_logw;
+    /* Optional layout hints (all three NULL: none).  When the model is a linear profile -- every state
+     * belongs to a position of a chain and every edge stays within two positions, except one loop-back
+     * edge pair (repeatHMM d1 / d2, S.py:339-346) -- the profile kernel (one warp per sequence, 4 positions
+     * per lane, neighbours in registers) serves it; otherwise the hints are ignored.
+     *   emit_pos[l]  : position of emitting state l;  emit_slot[l]: 0 match-like, 1 insert-like
+     *   chain_pos[c] : position of chain state c */
+    const int32_t *emit_pos;
+    const uint8_t *emit_slot;
+    const int32_t *chain_pos;
 } strique_hmm_desc;
 
 typedef struct {
@@ -148,8 +157,9 @@ typedef struct {
 } strique_viterbi_result;
 
 int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc, int32_t *model_id);
-/* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, otherwise the team
- * kernel shape as wps*1000 + high_slots*100 + low_slots*10 + chain_slots (diagnostic) */
+/* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, 4000 = profile kernel
+ * (4 positions per lane), otherwise the team kernel shape as wps*1000 + high_slots*100 + low_slots*10 +
+ * chain_slots (diagnostic) */
 int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id);
 /*
  *   x, x_offsets : float64 samples of all sequences concatenated; [n_seq+1] offsets (host)

@@ -33,7 +33,24 @@ class HmmDesc(ctypes.Structure):
                 ('emit_kind', ctypes.c_void_p), ('emit_a', ctypes.c_void_p), ('emit_b', ctypes.c_void_p),
                 ('emit_flags', ctypes.c_void_p), ('chain_pred_logw', ctypes.c_void_p),
                 ('chain_in_ptr', ctypes.c_void_p), ('chain_in_src', ctypes.c_void_p), ('chain_in_logw', ctypes.c_void_p),
-                ('n_end', ctypes.c_int32), ('end_src', ctypes.c_void_p), ('end_logw', ctypes.c_void_p)]
+                ('n_end', ctypes.c_int32), ('end_src', ctypes.c_void_p), ('end_logw', ctypes.c_void_p),
+                ('emit_pos', ctypes.c_void_p), ('emit_slot', ctypes.c_void_p), ('chain_pos', ctypes.c_void_p)]
+
+
+def hmm_desc(c):
+    """strique_hmm_desc of a CompiledHMM -> (desc, arrays that must stay alive while it is used)."""
+    keep = [np.ascontiguousarray(a) for a in (c.in_ptr, c.in_src, c.in_logw, c.emit_kind, c.emit_a, c.emit_b,
+                                              c.emit_flags, c.chain_pred_logw, c.chain_in_ptr, c.chain_in_src,
+                                              c.chain_in_logw, c.end_src, c.end_logw)]
+    hints = [None, None, None]
+    if getattr(c, 'emit_pos', None) is not None:
+        hints = [np.ascontiguousarray(c.emit_pos, dtype=np.int32), np.ascontiguousarray(c.emit_slot, dtype=np.uint8),
+                 np.ascontiguousarray(c.chain_pos, dtype=np.int32)]
+        keep += hints
+    d = HmmDesc(c.n_emit, c.n_chain, *[a.ctypes.data for a in keep[:11]], len(c.end_src),
+                keep[11].ctypes.data, keep[12].ctypes.data,
+                *[(a.ctypes.data if a is not None else None) for a in hints])
+    return d, keep
 
 
 class TargetDesc(ctypes.Structure):
@@ -218,17 +235,13 @@ class Context:
     # -- boundary #2 ------------------------------------------------------------------------------
     def hmm_create(self, c):
         """Register a compiled HMM (strique_b200.hmm.CompiledHMM) -> model id."""
-        keep = [np.ascontiguousarray(a) for a in (c.in_ptr, c.in_src, c.in_logw, c.emit_kind, c.emit_a, c.emit_b,
-                                                  c.emit_flags, c.chain_pred_logw, c.chain_in_ptr, c.chain_in_src,
-                                                  c.chain_in_logw, c.end_src, c.end_logw)]
-        d = HmmDesc(c.n_emit, c.n_chain, *[a.ctypes.data for a in keep[:11]], len(c.end_src),
-                    keep[11].ctypes.data, keep[12].ctypes.data)
+        d, keep = hmm_desc(c)
         mid = ctypes.c_int32(-1)
         self.check(self.lib.strique_hmm_create(self.handle, ctypes.byref(d), ctypes.byref(mid)), 'strique_hmm_create')
         return mid.value
 
     def hmm_kernel_shape(self, model_id):
-        """0: generic Viterbi kernel; else team-kernel shape wps*1000 + nh*100 + nl*10 + qc."""
+        """0: generic Viterbi kernel; 4000: profile kernel; else team-kernel shape wps*1000 + nh*100 + nl*10 + qc."""
         return int(self.lib.strique_hmm_kernel_shape(self.handle, model_id))
 
     def viterbi_batch(self, model_id, sequences, want_path=False):

@@ -145,7 +145,8 @@ int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out) {
     ctx->owned.push_back(dperm);
     m.blob = (const unsigned char *)dblob;
     m.perm = (const int32_t *)dperm;
-    return viterbi_fast_pack(ctx, d, out);
+    TRY(viterbi_fast_pack(ctx, d, out));
+    return viterbi_profile_pack(ctx, d, out);
 }
 
 // Decodes n_seq device-resident sequences, sequence s with model ctx->models[seq_model[s]].
@@ -174,17 +175,21 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     TRY(d_bpoff.ensure(ctx, (size_t)n_seq * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_xoff.p, x_off_host, (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     auto len = [&](int s) { return x_off_host[s + 1] - x_off_host[s]; };
+    // STRIQUE_VITERBI_GENERIC / STRIQUE_VITERBI_TEAM force the generic / the team kernel (A/B parity tests)
     const bool force_generic = getenv("STRIQUE_VITERBI_GENERIC") != nullptr;
-    // ---- groups: one per team-kernel shape, one per model for the generic kernel -----------------------
-    struct Group { bool fast; VitFastShape shape; int model; std::vector<int32_t> ids; };
+    const bool force_team = getenv("STRIQUE_VITERBI_TEAM") != nullptr;
+    // ---- groups: all profile-kernel models, one per team-kernel shape, one per model for the generic kernel
+    struct Group { bool fast; VitFastShape shape; int model; bool profile; std::vector<int32_t> ids; };
     std::vector<Group> groups;
     for (int s = 0; s < n_seq; ++s) {
         const HmmModel &m = *ctx->models[seq_model[s]];
-        const bool fast = m.shape.wps > 0 && !force_generic;
+        const bool profile = m.has_profile && !force_generic && !force_team;
+        const bool fast = !profile && m.shape.wps > 0 && !force_generic;
         Group *g = nullptr;
         for (Group &c : groups)
-            if (c.fast == fast && (fast ? c.shape == m.shape : c.model == seq_model[s])) { g = &c; break; }
-        if (!g) { groups.push_back(Group{fast, m.shape, seq_model[s], {}}); g = &groups.back(); }
+            if (c.profile == profile && c.fast == fast &&
+                (profile || (fast ? c.shape == m.shape : c.model == seq_model[s]))) { g = &c; break; }
+        if (!g) { groups.push_back(Group{fast, m.shape, seq_model[s], profile, {}}); g = &groups.back(); }
         g->ids.push_back(s);
         ctx->last_viterbi_edges += len(s) * m.n_edges;
     }
@@ -198,7 +203,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     std::vector<int64_t> bpoff(n_seq, 0);
     for (Group &g : groups) {
         std::stable_sort(g.ids.begin(), g.ids.end(), [&](int a, int b) { return len(a) > len(b); });
-        const int64_t unit = g.fast ? 4 : 8;                               // bytes per back-pointer word
+        const int64_t unit = (g.fast || g.profile) ? 4 : 8;                // bytes per back-pointer word
         const int64_t words_per_step = g.fast ? g.shape.wps * 32 : 32;
         size_t i0 = 0;
         while (i0 < g.ids.size()) {
@@ -216,7 +221,26 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
             TRY(d_order.ensure(ctx, (size_t)n * 4));
             CUDA_TRY(ctx, cudaMemcpyAsync(d_bpoff.p, bpoff.data(), (size_t)n_seq * 8, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
-            if (!g.fast) {
+            if (g.profile) {
+                // one warp per sequence, longest first; models of all loci / strands in one launch
+                DevBuf &d_smodel = ctx->buf("vit.seq_model"), &d_pmodels = ctx->buf("vit.prof_models");
+                std::vector<VitProfModelDev> pm(n_models);
+                for (int i = 0; i < n_models; ++i)
+                    if (ctx->models[i]->has_profile) pm[i] = ctx->models[i]->profile; else memset(&pm[i], 0, sizeof(pm[i]));
+                TRY(d_smodel.ensure(ctx, (size_t)n_seq * 4));
+                TRY(d_pmodels.ensure(ctx, (size_t)n_models * sizeof(VitProfModelDev)));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_smodel.p, seq_model, (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_pmodels.p, pm.data(), pm.size() * sizeof(VitProfModelDev), cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+                VitProfBatch b;
+                b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
+                b.seq_model = d_smodel.as<int32_t>(); b.n_seq = n; b.models = d_pmodels.as<VitProfModelDev>();
+                b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
+                b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
+                b.queue = d_queue.as<int>();
+                TRY(viterbi_profile_launch(ctx, b));
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // pm is read by the async copy
+            } else if (!g.fast) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
                 VitBatch b;
                 b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.n_seq = n; b.order = d_order.as<int32_t>();
@@ -292,6 +316,7 @@ extern "C" int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc
 
 extern "C" int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id) {
     if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size()) return -1;
+    if (ctx->models[model_id]->has_profile) return 4000;
     const VitFastShape &s = ctx->models[model_id]->shape;
     return s.wps * 1000 + s.nh * 100 + s.nl * 10 + s.qc;
 }

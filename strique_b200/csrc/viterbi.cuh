@@ -17,6 +17,7 @@
 // (one 8/16-byte word per lane per step, coalesced), traceback by the same warp.
 #pragma once
 #include "common.cuh"
+#include "profile_core.h"
 
 namespace strique {
 
@@ -58,11 +59,30 @@ struct VitFastShape {              // which instantiation of the team kernel ser
     bool operator==(const VitFastShape &o) const { return wps == o.wps && nh == o.nh && nl == o.nl && qc == o.qc; }
 };
 
+// Device view of a model packed for the profile kernel (viterbi_profile.cu, profile_pack.h): the per-lane
+// constant table, per (position, slot) emission / flag tables for the slow emission path and the
+// traceback, the long-range (repeat loop) sources and the END edges.
+struct VitProfModelDev {
+    const double *tab;             // [pf::K_TOTAL][32]
+    const uint8_t *em_kind;        // [pf::NPOS * 2], index position * 2 + slot
+    const double *em_a, *em_b, *em_c;
+    const uint8_t *flags;
+    const int32_t *state_id;       // caller's emitting state id
+    pf::TraceCfg trace;
+    double lo, hi;                 // samples inside [lo, hi] take the fast emission path
+    int p_start;                   // START = match slot of this position, value 0 in column 0
+    int n_end;
+    int32_t end_p[16], end_slot[16];
+    double end_w[16];
+};
+
 struct HmmModel {                 // host-side handle; device arrays owned by the context
     VitModelDev dev;
     int64_t n_edges = 0;          // in-edges of emitting + chain states (work unit of the Viterbi stage)
     VitFastShape shape;
     VitFastModelDev fast;
+    bool has_profile = false;
+    VitProfModelDev profile;
 };
 
 struct VitCtaTask {                // <= 8/WPS sequences of one model, consecutive in `order`
@@ -86,6 +106,21 @@ struct VitFastBatch {
 };
 
 
+struct VitProfBatch {
+    const double *x;
+    const int64_t *x_off;
+    const int32_t *order;          // [n_seq] sequence ids, longest first
+    const int32_t *seq_model;      // [all sequences] model index of a sequence id
+    int n_seq;
+    const VitProfModelDev *models; // device array indexed by model
+    uint32_t *bp;
+    const int64_t *bp_off;         // [all sequences] offset in 32-bit words (per sequence: (T+1) * 32 words)
+    VitResult *res;
+    uint8_t *pattern;
+    uint16_t *path;
+    int *queue;
+};
+
 struct VitBatch {
     const double *x;            // normalised samples, all sequences concatenated
     const int64_t *x_off;       // [n_seq + 1]
@@ -104,6 +139,9 @@ int viterbi_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
 int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
 int viterbi_fast_launch(strique_ctx *ctx, const VitFastShape &shape, const VitFastBatch &b);
 int viterbi_fast_teams(const VitFastShape &shape);   // sequences per CTA task
+// profile kernel: packs the model if its layout hints describe a linear profile (sets m->has_profile), launch
+int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
+int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b);
 // decodes sequences of several models in one pass: seq_model[s] indexes ctx->models
 int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
                              int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,

@@ -1,0 +1,285 @@
+// Profile Viterbi: the throughput kernel of boundary #2 for the reference's linear profile HMMs.
+//
+// Replaces pomegranate 0.10.0 `HiddenMarkovModel.viterbi` behind flankedRepeatHMM.count_repeats
+// (reference scripts/STRique.py:433-441, 374-378; topology 201-431).  float64 throughout, one add per
+// edge, strict-'>' maxima (profile_core.h holds the lane arithmetic, shared with the host emulator of
+// the test suite; profile_pack.h recognises and packs the model).
+//
+// Mapping: ONE WARP decodes one sequence; lane l owns profile positions 4l..4l+3 (match, insert and
+// delete state each), so
+//   * every regular edge reads a register of the same lane or one of three values shuffled up from
+//     lane l-1 -- no shared-memory value columns, no barriers;
+//   * the repeat loop (d2 -> M_0, d1 -> s1) is one indexed shuffle pair;
+//   * in-edge weights of the emitting states live in registers, the delete-chain / emission constants in a
+//     per-warp shared-memory table read with conflict-free LDS.64 [lane*8 + const];
+//   * the delete chain of a column is a max-plus scan: sequential inside the lane, Kogge-Stone across
+//     lanes; the E1 part of the NEXT column (all edges from emitting states) sits in the same basic
+//     block and fills the shuffle / fp64 latencies of the scan;
+//   * back-pointers: one byte per position -> ONE 32-bit word per lane per column = 128 B per time step,
+//     coalesced; traceback by the same warp over rows staged 32 at a time with cp.async.
+// Warps are independent: each pulls sequences (longest first) from a global queue.
+#include <math.h>
+
+#include <algorithm>
+
+#include "profile_pack.h"
+#include "viterbi.cuh"
+
+namespace strique {
+
+namespace {
+
+constexpr int PROF_WARPS = 4;                       // warps per CTA
+constexpr int PROF_STAGE_ROWS = 32;
+constexpr int PROF_AUX_BYTES = pf::K_NAUX * 32 * 8;
+constexpr int PROF_STAGE_BYTES = PROF_STAGE_ROWS * 32 * 4;
+constexpr int PROF_WARP_BYTES = PROF_AUX_BYTES + PROF_STAGE_BYTES;
+static_assert(PROF_STAGE_BYTES >= 3 * pf::NPOS * 8, "the END gather reuses the stage area");
+
+struct AuxShared {                                  // tab(k) of this lane, k >= K_NREG
+    const double *base;                             // &aux[lane]
+    __device__ __forceinline__ double operator()(int k) const { return base[(k - pf::K_NREG) * 32]; }
+};
+struct TabGlobal {
+    const double *base;                             // &tab[lane]
+    __device__ __forceinline__ double operator()(int k) const { return __ldg(base + k * 32); }
+};
+
+__device__ __forceinline__ double pick4(const double v[pf::P], int q) {
+    return q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : v[3]));
+}
+
+__global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(VitProfBatch b) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem + (size_t)warp * PROF_WARP_BYTES;
+    double *aux_s = reinterpret_cast<double *>(wbase);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + PROF_AUX_BYTES);
+    const AuxShared aux{aux_s + lane};
+    const double NINF = pf::ninf();
+    const unsigned FULL = 0xffffffffu;
+
+    pf::Regs R;
+    int cur_model = -1;
+    // warp-uniform model scalars
+    int p_start = 0, xlane = 0, xq = 0, xm_slot = 0, xd_slot = 0;
+    double lo = 0.0, hi = 0.0;
+
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(b.queue, 1);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= b.n_seq) break;
+        const int seq = b.order[task];
+        const int mi = b.seq_model[seq];
+        const VitProfModelDev &m = b.models[mi];
+        if (mi != cur_model) {
+            cur_model = mi;
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < pf::K_NAUX; ++k) aux_s[k * 32 + lane] = __ldg(m.tab + (pf::K_NREG + k) * 32 + lane);
+            pf::load_regs(TabGlobal{m.tab + lane}, R);
+            p_start = m.p_start;
+            const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+            xlane = xp / pf::P;
+            xq = xp % pf::P;
+            xm_slot = m.trace.xm_src_slot;
+            xd_slot = m.trace.xd_src_slot;
+            lo = m.lo;
+            hi = m.hi;
+            __syncwarp();
+        }
+        const int64_t xo = b.x_off[seq];
+        const int T = (int)(b.x_off[seq + 1] - xo);
+        const double *x = b.x + xo;
+        uint32_t *bp = b.bp + b.bp_off[seq];
+
+        pf::State S;
+#pragma unroll
+        for (int q = 0; q < pf::P; ++q) {
+            S.M[q] = (lane * pf::P + q == p_start) ? 0.0 : NINF;   // START: value 0 before the first sample only
+            S.I[q] = S.D[q] = S.partM[q] = S.partI[q] = NINF;
+        }
+        S.Dprev = NINF;
+        S.pbits = 0u;
+
+        // E1 of the next column + delete chain of the column just finished (one basic block)
+        auto block = [&]() -> uint32_t {
+            const double pM3 = __shfl_up_sync(FULL, S.M[3], 1);
+            const double pI3 = __shfl_up_sync(FULL, S.I[3], 1);
+            const double pM2 = __shfl_up_sync(FULL, S.M[2], 1);
+            const double vm = pick4(S.M, xq), vi = pick4(S.I, xq);
+            const double xm = __shfl_sync(FULL, xm_slot ? vi : vm, xlane);
+            const double xd = __shfl_sync(FULL, xd_slot ? vi : vm, xlane);
+            pf::e1(R, S, pM3, pI3, pM2, xm);
+            double a[pf::P], A;
+            uint32_t bits = pf::d_entry(aux, S, pM3, pI3, xd, a, A);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const double Al = __shfl_up_sync(FULL, A, 1 << r);
+                A = pf::d_round(aux, A, Al, r);
+            }
+            const double Din = __shfl_up_sync(FULL, A, 1);
+            bits |= pf::d_final(aux, S, a, Din);
+            return bits;
+        };
+
+        bp[lane] = block();                                  // column 0: delete chain from START
+        double xcur = T > 0 ? __ldg(x) : 0.0;
+#pragma unroll 1
+        for (int t = 1; t <= T; ++t) {
+            const double xnext = t < T ? __ldg(x + t) : 0.0;
+            double eM[pf::P], eI[pf::P];
+            if (xcur >= lo && xcur <= hi) {
+                pf::emissions_fast(aux, xcur, eM, eI);
+            } else {                                         // outside a Uniform range or NaN: general form
+#pragma unroll
+                for (int q = 0; q < pf::P; ++q) {
+                    const int i0 = (lane * pf::P + q) * 2;
+                    eM[q] = pf::emission_slow(m.em_kind[i0], m.em_a[i0], m.em_b[i0], m.em_c[i0], xcur);
+                    eI[q] = pf::emission_slow(m.em_kind[i0 + 1], m.em_a[i0 + 1], m.em_b[i0 + 1], m.em_c[i0 + 1], xcur);
+                }
+            }
+            const uint32_t word = pf::e2_emit(R, S, eM, eI);
+            const uint32_t dbits = block();
+            bp[(size_t)t * 32 + lane] = word | dbits;
+            xcur = xnext;
+        }
+
+        // ---- END edges: log p = max(v[T][src] + w), first maximum ------------------------------------
+        __syncwarp();
+        double *vals = reinterpret_cast<double *>(stage);
+#pragma unroll
+        for (int q = 0; q < pf::P; ++q) {
+            vals[lane * pf::P + q] = S.M[q];
+            vals[pf::NPOS + lane * pf::P + q] = S.I[q];
+            vals[2 * pf::NPOS + lane * pf::P + q] = S.D[q];
+        }
+        __syncwarp();
+        double best = NINF;
+        int barg = -1;
+        if (lane < m.n_end) {
+            const double cand = vals[m.end_slot[lane] * pf::NPOS + m.end_p[lane]] + m.end_w[lane];
+            if (cand > best) { best = cand; barg = lane; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_down_sync(FULL, best, off);
+            const int oa = __shfl_down_sync(FULL, barg, off);
+            if (ob > best || (ob == best && oa >= 0 && (barg < 0 || oa < barg))) { best = ob; barg = oa; }
+        }
+        best = __shfl_sync(FULL, best, 0);
+        barg = __shfl_sync(FULL, barg, 0);
+        __syncwarp();
+
+        // ---- traceback (all lanes walk in lock step; lane 0 writes) ----------------------------------
+        VitResult r;
+        r.logp = best; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 0; r.reserved = 0;
+        if (!(best > NINF) || barg < 0) {
+            r.status = 1;
+        } else {
+            const pf::TraceCfg tc = m.trace;
+            int p = m.end_p[barg], slot = m.end_slot[barg], t = T;
+            uint8_t *pat = b.pattern ? b.pattern + xo : nullptr;
+            uint16_t *path = b.path ? b.path + xo : nullptr;
+            bool in_group = false;
+            uint8_t last_mod = '0';
+            int plen = 0;
+            int stage_lo = T + 1;                 // rows [stage_lo, stage_lo + 32) are staged
+            long long guard = (long long)(T + 2) * (pf::NPOS + 2);
+            while (!(slot == 0 && p == p_start)) {
+                if (--guard < 0 || p < 0 || p >= pf::NPOS || t < 0) { r.status = 2; break; }
+                if (t < stage_lo) {
+                    // stage the next rows: 16-byte async copies, all in flight at once
+                    __syncwarp();
+                    stage_lo = t - (PROF_STAGE_ROWS - 1) > 0 ? t - (PROF_STAGE_ROWS - 1) : 0;
+                    const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)stage_lo * 32);
+                    const int nvec = (t - stage_lo + 1) * 8;
+                    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage);
+#pragma unroll
+                    for (int i = 0; i < PROF_STAGE_ROWS * 8 / 32; ++i)
+                        if (lane + 32 * i < nvec)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (lane + 32 * i) * 16),
+                                         "l"(src + lane + 32 * i)
+                                         : "memory");
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();
+                }
+                if (slot < 2) {
+                    if (t < 1) { r.status = 2; break; }
+                    const int idx = p * 2 + slot;
+                    const unsigned fl = m.flags[idx];
+                    if (fl & HMM_FLAG_COUNT) ++r.n_count;
+                    if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - 1; }
+                    if (fl & HMM_FLAG_SEP) {
+                        if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; in_group = false; }
+                    } else {
+                        in_group = true;
+                        last_mod = (fl & HMM_FLAG_MOD) ? '1' : '0';
+                    }
+                    if (path && lane == 0) path[t - 1] = (uint16_t)m.state_id[idx];
+                }
+                pf::back(stage[(t - stage_lo) * 32 + (p >> 2)], tc, p, slot, t);
+            }
+            if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; }
+            if (r.status == 0 && t != 0) r.status = 2;
+            r.pattern_len = plen;
+        }
+        if (lane == 0) b.res[seq] = r;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b) {
+    if (b.n_seq == 0) return STRIQUE_OK;
+    const size_t smem = (size_t)PROF_WARPS * PROF_WARP_BYTES;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(viterbi_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_kernel, PROF_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = ctx->num_sms * per_sm;
+    const int need = (b.n_seq + PROF_WARPS - 1) / PROF_WARPS;
+    if (grid > need) grid = need;
+    viterbi_profile_kernel<<<grid, PROF_WARPS * 32, smem, ctx->stream>>>(b);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+// Packs the model for the profile kernel when its layout hints describe a linear profile (profile_pack.h);
+// otherwise leaves m->profile.tab == nullptr.
+int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m) {
+    m->has_profile = false;
+    ProfileImage img;
+    std::string why;
+    if (!profile_pack(d, &img, &why)) return STRIQUE_OK;
+    VitProfModelDev &f = m->profile;
+    memset(&f, 0, sizeof(f));
+    auto upload = [&](const void *src, size_t bytes, const void **dst) -> int {
+        void *p = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+        CUDA_TRY(ctx, cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        ctx->owned.push_back(p);
+        *dst = p;
+        return STRIQUE_OK;
+    };
+    TRY(upload(img.tab.data(), img.tab.size() * 8, (const void **)&f.tab));
+    TRY(upload(img.em_kind.data(), img.em_kind.size(), (const void **)&f.em_kind));
+    TRY(upload(img.em_a.data(), img.em_a.size() * 8, (const void **)&f.em_a));
+    TRY(upload(img.em_b.data(), img.em_b.size() * 8, (const void **)&f.em_b));
+    TRY(upload(img.em_c.data(), img.em_c.size() * 8, (const void **)&f.em_c));
+    TRY(upload(img.flags.data(), img.flags.size(), (const void **)&f.flags));
+    TRY(upload(img.state_id.data(), img.state_id.size() * 4, (const void **)&f.state_id));
+    f.trace = img.trace;
+    f.lo = img.lo;
+    f.hi = img.hi;
+    f.p_start = img.p_off - 1;
+    f.n_end = img.n_end;
+    for (int e = 0; e < img.n_end; ++e) { f.end_p[e] = img.end_p[e]; f.end_slot[e] = img.end_slot[e]; f.end_w[e] = img.end_w[e]; }
+    m->has_profile = true;
+    return STRIQUE_OK;
+}
+
+}  // namespace strique

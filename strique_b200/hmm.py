@@ -34,6 +34,8 @@ class Graph(object):
         self.start = self.state('start')
         self.end = self.state('end')
         self.counted = set()
+        self.hint = {}             # state -> (segment name, index in segment, slot 0 M / 1 I / 2 D)
+        self.layout = None         # segment names in chain order: enables the profile-kernel layout hints
 
     def state(self, name, dist=None):
         self.names.append(name)
@@ -66,6 +68,11 @@ def add_profile(g, sequence, pm, probs, prefix, no_silent=False, std_scale=1.0, 
     I = [g.uniform(tag[i] + 'i', pm.model_min, pm.model_max) for i in range(n)]
     D = [] if no_silent else [g.state(tag[i] + 'd') for i in range(n)]
     s1, s2, e1, e2 = (g.state(prefix + x) for x in ('s1', 's2', 'e1', 'e2'))
+    for i in range(n):
+        g.hint[M[i]] = (prefix, i, 0)
+        g.hint[I[i]] = (prefix, i, 1)
+        if D:
+            g.hint[D[i]] = (prefix, i, 2)
     last = n - 1
     for i in range(n):
         g.link(M[i], M[i], tp['match_loop'])
@@ -125,6 +132,8 @@ def add_repeat_loop(g, repeat, pm, probs, prefix, std_scale=1.0, std_offset=0.0)
     g.link(d1, s1, 1 - tp['leave_repeat'])
     g.link(d2, s2, 1 - tp['leave_repeat'])
     g.counted.update((d1, d2))
+    g.hint[d2] = (prefix + 'dummy', 0, 0)       # one extra position after the unit: d2 match-like, d1 insert-like
+    g.hint[d1] = (prefix + 'dummy', 0, 1)
     return s1, s2, e1, e2, repeat_offset
 
 
@@ -150,6 +159,7 @@ def flanked_repeat_graph(repeat, prefix, suffix, pm, config=None):
     g.link(r[3], s[1], 1)
     g.link(s[2], g.end, 1)
     g.link(s[3], g.end, 1)
+    g.layout = ['prefix', 'repeat', 'repeatdummy', 'suffix']
     return g, (c * 2 - 1) - r[4]
 
 
@@ -325,4 +335,19 @@ def compile_graph(g):
     c.end_src = np.array([vid(a) for a, _ in end_edges], dtype=np.int32)
     c.end_logw = np.array([w for _, w in end_edges], dtype=np.float64)
     c.n_edges = int(len(c.in_src) + sum(len(x) for x in chain_in) + int(np.sum(np.isfinite(chain_pred[:C]))))
+    # layout hints for the profile kernel (include/strique_b200.h): position = offset of the segment + index
+    c.emit_pos = c.emit_slot = c.chain_pos = None
+    if g.layout and all(s in g.hint for s in emitting + order):
+        size = {}
+        for s in emitting + order:
+            seg, i, _ = g.hint[s]
+            size[seg] = max(size.get(seg, 0), i + 1)
+        if set(size) <= set(g.layout):
+            base, at = {}, 0
+            for seg in g.layout:
+                base[seg] = at
+                at += size.get(seg, 0)
+            c.emit_pos = np.array([base[g.hint[s][0]] + g.hint[s][1] for s in emitting], dtype=np.int32)
+            c.emit_slot = np.array([g.hint[s][2] for s in emitting], dtype=np.uint8)
+            c.chain_pos = np.array([base[g.hint[s][0]] + g.hint[s][1] for s in order] or [0], dtype=np.int32)
     return c

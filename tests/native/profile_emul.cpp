@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE (not product code): runs the profile Viterbi kernel's lane arithmetic
+// (strique_b200/csrc/profile_core.h) and model packer (profile_pack.h) on the host, 32 simulated lanes in
+// lock step, shuffles replaced by array reads -- the same phases in the same order as
+// strique_b200/csrc/viterbi_profile.cu.  Lets the CPU test suite check packing, back-pointer encoding and
+// traceback against the oracle without a GPU.  Nothing under strique_b200/ links or calls this.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../strique_b200/csrc/profile_pack.h"
+
+using namespace strique;
+
+namespace {
+struct TabLane {
+    const double *tab;
+    int lane;
+    double operator()(int k) const { return tab[(size_t)k * 32 + lane]; }
+};
+}  // namespace
+
+extern "C" int strique_test_profile_fits(const strique_hmm_desc *d, char *why, int why_cap) {
+    ProfileImage img;
+    std::string w;
+    const bool ok = profile_pack(d, &img, &w);
+    if (why && why_cap > 0) { strncpy(why, w.c_str(), why_cap - 1); why[why_cap - 1] = 0; }
+    return ok ? img.np : 0;
+}
+
+// status: 0 ok, 1 impossible, 2 internal error, -1 model does not fit
+extern "C" int strique_test_profile_emulate(const strique_hmm_desc *d, const double *x, int64_t T, double *logp,
+                                            int32_t *n_count, int32_t *t_first, int32_t *t_last, int32_t *path) {
+    ProfileImage img;
+    if (!profile_pack(d, &img, nullptr)) return -1;
+    const double NINF = pf::ninf();
+    pf::Regs regs[32];
+    pf::State st[32];
+    TabLane aux[32];
+    for (int l = 0; l < 32; ++l) {
+        aux[l] = TabLane{img.tab.data(), l};
+        pf::load_regs(aux[l], regs[l]);
+        for (int q = 0; q < pf::P; ++q) st[l].M[q] = st[l].I[q] = st[l].D[q] = st[l].partM[q] = st[l].partI[q] = NINF;
+        st[l].Dprev = NINF;
+        st[l].pbits = 0;
+    }
+    const int p_start = img.p_off - 1;
+    st[p_start / pf::P].M[p_start % pf::P] = 0.0;
+    std::vector<uint32_t> bp((size_t)(T + 1) * 32);
+    auto val = [&](int p, int slot) {
+        const pf::State &s = st[p / pf::P];
+        return slot == 0 ? s.M[p % pf::P] : (slot == 1 ? s.I[p % pf::P] : s.D[p % pf::P]);
+    };
+    auto block = [&](uint32_t *dbits) {     // E1 of the next column + delete chain of this column
+        double pM3[32], pI3[32], pM2[32], a[32][pf::P], A[32];
+        const double xm = img.trace.xm_src_p >= 0 ? val(img.trace.xm_src_p, img.trace.xm_src_slot) : NINF;
+        const double xd = img.trace.xd_src_p >= 0 ? val(img.trace.xd_src_p, img.trace.xd_src_slot) : NINF;
+        for (int l = 0; l < 32; ++l) {      // __shfl_up(.., 1): lane 0 keeps its own value
+            const int s = l > 0 ? l - 1 : 0;
+            pM3[l] = st[s].M[3]; pI3[l] = st[s].I[3]; pM2[l] = st[s].M[2];
+        }
+        for (int l = 0; l < 32; ++l) {
+            pf::e1(regs[l], st[l], pM3[l], pI3[l], pM2[l], xm);
+            dbits[l] = pf::d_entry(aux[l], st[l], pM3[l], pI3[l], xd, a[l], A[l]);
+        }
+        for (int r = 0; r < 5; ++r) {
+            double An[32];
+            for (int l = 0; l < 32; ++l) An[l] = pf::d_round(aux[l], A[l], A[l >= (1 << r) ? l - (1 << r) : l], r);
+            memcpy(A, An, sizeof(A));
+        }
+        double Din[32];
+        for (int l = 0; l < 32; ++l) Din[l] = A[l > 0 ? l - 1 : 0];
+        for (int l = 0; l < 32; ++l) dbits[l] |= pf::d_final(aux[l], st[l], a[l], Din[l]);
+    };
+    uint32_t dbits[32];
+    block(dbits);
+    for (int l = 0; l < 32; ++l) bp[l] = dbits[l];
+    for (int64_t t = 1; t <= T; ++t) {
+        const double xt = x[t - 1];
+        uint32_t word[32];
+        const bool fast = xt >= img.lo && xt <= img.hi;
+        for (int l = 0; l < 32; ++l) {
+            double eM[pf::P], eI[pf::P];
+            if (fast) {
+                pf::emissions_fast(aux[l], xt, eM, eI);
+            } else {
+                for (int q = 0; q < pf::P; ++q) {
+                    const int i0 = (l * pf::P + q) * 2;
+                    eM[q] = pf::emission_slow(img.em_kind[i0], img.em_a[i0], img.em_b[i0], img.em_c[i0], xt);
+                    eI[q] = pf::emission_slow(img.em_kind[i0 + 1], img.em_a[i0 + 1], img.em_b[i0 + 1], img.em_c[i0 + 1], xt);
+                }
+            }
+            word[l] = pf::e2_emit(regs[l], st[l], eM, eI);
+        }
+        block(dbits);
+        for (int l = 0; l < 32; ++l) bp[(size_t)t * 32 + l] = word[l] | dbits[l];
+    }
+    double best = NINF;
+    int barg = -1;
+    for (int e = 0; e < img.n_end; ++e) {
+        const double cand = val(img.end_p[e], img.end_slot[e]) + img.end_w[e];
+        if (cand > best) { best = cand; barg = e; }
+    }
+    *logp = best;
+    *n_count = 0; *t_first = -1; *t_last = -1;
+    if (!(best > NINF) || barg < 0) return 1;
+    int p = img.end_p[barg], slot = img.end_slot[barg], t = (int)T;
+    long long guard = (long long)(T + 2) * (pf::NPOS + 2);
+    while (!(slot == 0 && p == p_start)) {
+        if (--guard < 0 || p < 0 || p >= pf::NPOS || t < 0) return 2;
+        if (slot < 2) {
+            if (t < 1) return 2;
+            const int idx = p * 2 + slot;
+            if (img.state_id[idx] < 0) return 2;
+            if (img.flags[idx] & 1) ++*n_count;
+            if (img.flags[idx] & 2) { if (*t_last < 0) *t_last = t - 1; *t_first = t - 1; }
+            if (path) path[t - 1] = img.state_id[idx];
+        }
+        pf::back(bp[(size_t)t * 32 + p / pf::P], img.trace, p, slot, t);
+    }
+    return t == 0 ? 0 : 2;
+}

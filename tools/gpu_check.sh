@@ -17,6 +17,6 @@ echo "== ncu full: scan"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:align_scan -c 1 -f -o "$OUT/scan_$TAG" \
     python bench.py --batch 2048 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_scan_$TAG.log" 2>&1
 echo "== ncu full: viterbi"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:viterbi_team -c 1 -f -o "$OUT/viterbi_$TAG" \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:viterbi_profile -c 1 -f -o "$OUT/viterbi_$TAG" \
     python bench.py --batch 2048 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_viterbi_$TAG.log" 2>&1
 ls -la "$OUT"
