@@ -34,27 +34,31 @@ namespace pf {
 constexpr int P = 4;            // positions per lane
 constexpr int NPOS = 128;       // positions per model (32 lanes x P)
 
-// Per-lane constant table of a packed model: tab[k * 32 + lane], k below.
+// Per-lane constant table of a packed model: logical layout tab[k * 32 + lane], k below.  Entries the kernel
+// reads together sit at (even, odd) indices so that it can fetch them as one 16-byte pair (Tab::pair).
 enum : int {
-    K_WM = 0,                   // [q][6]: self, M-1, I-1, D-1, I, M-2
-    K_WI = K_WM + P * 6,        // [q][3]: self, M, D
-    K_WXM = K_WI + P * 3,       // X_M weight (target: in-lane position 0)
-    K_NREG = K_WXM + 1,         // ---- everything above is held in registers by the kernel ----
-    K_WD = K_NREG,              // [q][3]: M-1, I-1, D-1 (chain hop)
-    K_WXD = K_WD + P * 3,
-    K_EMU = K_WXD + 1,          // [q] Normal mean (0 for Uniform / dead)
-    K_EC0 = K_EMU + P,          // [q] -log(sigma sqrt(2 pi)) | -log(hi - lo) | 0
-    K_EC2 = K_EC0 + P,          // [q] 1 / (2 sigma^2) | 0
-    K_EI = K_EC2 + P,           // [q] I-slot emission -log(hi - lo)
-    K_CWR = K_EI + P,           // [5] summed hop weights seen by the rounds of the cross-lane scan
-    K_TOTAL = K_CWR + 5,
+    K_WMR = 0,                  // [q][4]: in-edges of M_p from  M_p (self), M_{p-1}, I_{p-1}, I_p
+    K_NREG = K_WMR + P * 4,     // ---- everything above is held in registers by the kernel ----
+    K_WI = K_NREG,              // [q] pair: in-edges of I_p from  I_p (self), M_p
+    K_E2 = K_WI + P * 2,        // [q] pair: D_{p-1} -> M_p, D_p -> I_p
+    K_WM2 = K_E2 + P * 2,       // [q]: M_{p-2} -> M_p
+    K_WX = K_WM2 + P,           // pair: X_M weight, X_D weight (targets: in-lane position 0)
+    K_WD = K_WX + 2,            // [q] pair: entries of D_p from  M_{p-1}, I_{p-1}
+    K_WH = K_WD + P * 2,        // [q]: chain hop D_{p-1} -> D_p
+    K_EM = K_WH + P,            // [q] pair: Normal mean (0 for Uniform / dead), 1 / (2 sigma^2) | 0
+    K_EC = K_EM + P * 2,        // [q] pair: -log(sigma sqrt(2 pi)) | -log(hi - lo) | 0, I-slot emission -log(hi - lo)
+    K_CWR = K_EC + P * 2,       // [5] summed hop weights seen by the rounds of the cross-lane scan (+ 1 pad)
+    K_TOTAL = K_CWR + 6,
     K_NAUX = K_TOTAL - K_NREG
+};
+static_assert(K_NREG % 2 == 0 && K_TOTAL % 2 == 0 && P % 2 == 0, "pairs must start at even indices");
+
+struct Pair {
+    double a, b;
 };
 
 struct Regs {                   // constants kept in registers
-    double wM[P][6];
-    double wI[P][3];
-    double wXM;
+    double wM[P][4];
 };
 
 struct State {
@@ -79,11 +83,8 @@ PF_HD void load_regs(const Tab &tab, Regs &r) {
 #pragma unroll
     for (int q = 0; q < P; ++q) {
 #pragma unroll
-        for (int d = 0; d < 6; ++d) r.wM[q][d] = tab(K_WM + q * 6 + d);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) r.wI[q][d] = tab(K_WI + q * 3 + d);
+        for (int d = 0; d < 4; ++d) r.wM[q][d] = tab(K_WMR + q * 4 + d);
     }
-    r.wXM = tab(K_WXM);
 }
 
 // Fast-path emissions (x inside every Uniform range, not NaN).
@@ -91,9 +92,10 @@ template <class Aux>
 PF_HD void emissions_fast(const Aux &aux, double x, double eM[P], double eI[P]) {
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const double dx = x - aux(K_EMU + q);
-        eM[q] = aux(K_EC0 + q) - (dx * dx) * aux(K_EC2 + q);
-        eI[q] = aux(K_EI + q);
+        const Pair em = aux.pair(K_EM + q * 2), ec = aux.pair(K_EC + q * 2);
+        const double dx = x - em.a;
+        eM[q] = ec.a - (dx * dx) * em.b;
+        eI[q] = ec.b;
     }
 }
 
@@ -109,13 +111,15 @@ PF_HD double emission_slow(int kind, double a, double b, double c, double x) {
 }
 
 // E2 + emission: finishes column t from the E1 maxima and the delete states of column t-1.
-PF_HD uint32_t e2_emit(const Regs &r, State &s, const double eM[P], const double eI[P]) {
+template <class Aux>
+PF_HD uint32_t e2_emit(const Aux &aux, State &s, const double eM[P], const double eI[P]) {
     uint32_t word = s.pbits;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const double dsrc = q == 0 ? s.Dprev : s.D[q - 1];
-        const double cm = dsrc + r.wM[q][3];
-        const double ci = s.D[q] + r.wI[q][2];
+        const Pair w = aux.pair(K_E2 + q * 2);
+        const double dsrc = q == 0 ? s.Dprev : s.D[q > 0 ? q - 1 : 0];
+        const double cm = dsrc + w.a;
+        const double ci = s.D[q] + w.b;
         double bm = s.partM[q], bi = s.partI[q];
         if (cm > bm) { bm = cm; word |= 8u << (8 * q); }
         if (ci > bi) { bi = ci; word |= 32u << (8 * q); }
@@ -125,33 +129,43 @@ PF_HD uint32_t e2_emit(const Regs &r, State &s, const double eM[P], const double
     return word;
 }
 
+// One node of a first-maximum tournament: the right candidate wins only when strictly greater, so the
+// earliest candidate of the sequential order wins ties whatever the shape of the tree.
+PF_HD void duel(double &v, uint32_t &arg, double vr, uint32_t argr) {
+    const bool gt = vr > v;
+    v = gt ? vr : v;
+    arg = gt ? argr : arg;
+}
+
 // E1 of the next column from the emitting values of the column just finished.
 // pM3 / pI3 / pM2: M, I of the last and M of the last-but-one position of the previous lane; xm: X_M source.
-PF_HD void e1(const Regs &r, State &s, double pM3, double pI3, double pM2, double xm) {
+// Candidate order (ties: first wins): 0 self, 1 M_{p-1}, 2 I_{p-1}, 3 I_p, 4 M_{p-2}, 5 X_M.
+template <class Aux>
+PF_HD void e1(const Regs &r, const Aux &aux, State &s, double pM3, double pI3, double pM2, double xm) {
     uint32_t bits = 0u;
+    const Pair wx = aux.pair(K_WX);
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const double m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
         const double i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
         const double m2 = q == 0 ? pM2 : (q == 1 ? pM3 : s.M[q > 1 ? q - 2 : 0]);
-        double best = s.M[q] + r.wM[q][0];
-        uint32_t arg = 0u;
-        double c = m1 + r.wM[q][1];
-        if (c > best) { best = c; arg = 1u; }
-        c = i1 + r.wM[q][2];
-        if (c > best) { best = c; arg = 2u; }
-        c = s.I[q] + r.wM[q][4];
-        if (c > best) { best = c; arg = 3u; }
-        c = m2 + r.wM[q][5];
-        if (c > best) { best = c; arg = 4u; }
-        if (q == 0) {
-            c = xm + r.wXM;
-            if (c > best) { best = c; arg = 5u; }
-        }
-        s.partM[q] = best;
-        bits |= arg << (8 * q);
-        double bi = s.I[q] + r.wI[q][0];
-        c = s.M[q] + r.wI[q][1];
+        const Pair wm2 = aux.pair(K_WM2 + (q & ~1));
+        const Pair wi = aux.pair(K_WI + q * 2);
+        double v01 = s.M[q] + r.wM[q][0];
+        uint32_t a01 = 0u;
+        duel(v01, a01, m1 + r.wM[q][1], 1u);
+        double v23 = i1 + r.wM[q][2];
+        uint32_t a23 = 2u;
+        duel(v23, a23, s.I[q] + r.wM[q][3], 3u);
+        double v45 = m2 + ((q & 1) ? wm2.b : wm2.a);
+        uint32_t a45 = 4u;
+        if (q == 0) duel(v45, a45, xm + wx.a, 5u);
+        duel(v01, a01, v23, a23);
+        duel(v01, a01, v45, a45);
+        s.partM[q] = v01;
+        bits |= a01 << (8 * q);
+        double bi = s.I[q] + wi.a;
+        const double c = s.M[q] + wi.b;
         if (c > bi) { bi = c; bits |= 16u << (8 * q); }
         s.partI[q] = bi;
     }
@@ -163,26 +177,25 @@ PF_HD void e1(const Regs &r, State &s, double pM3, double pI3, double pM2, doubl
 template <class Aux>
 PF_HD uint32_t d_entry(const Aux &aux, const State &s, double pM3, double pI3, double xd, double a[P], double &A) {
     uint32_t bits = 0u;
+    const Pair wx = aux.pair(K_WX);
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const double m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
         const double i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
-        double best = m1 + aux(K_WD + q * 3 + 0);
+        const Pair wd = aux.pair(K_WD + q * 2);
+        double best = m1 + wd.a;
         uint32_t arg = 0u;
-        double c = i1 + aux(K_WD + q * 3 + 1);
-        if (c > best) { best = c; arg = 1u; }
-        if (q == 0) {
-            c = xd + aux(K_WXD);
-            if (c > best) { best = c; arg = 2u; }
-        }
+        duel(best, arg, i1 + wd.b, 1u);
+        if (q == 0) duel(best, arg, xd + wx.b, 2u);
         a[q] = best;
         bits |= arg << (8 * q + 6);
-        if (q == 0) {
-            A = best;
-        } else {
-            const double t0 = A + aux(K_WD + q * 3 + 2);
-            A = best >= t0 ? best : t0;
-        }
+    }
+    const Pair h01 = aux.pair(K_WH), h23 = aux.pair(K_WH + 2);
+    A = a[0];
+#pragma unroll
+    for (int q = 1; q < P; ++q) {
+        const double t0 = A + (q == 1 ? h01.b : (q == 2 ? h23.a : h23.b));
+        A = a[q] >= t0 ? a[q] : t0;
     }
     return bits;
 }
@@ -190,7 +203,8 @@ PF_HD uint32_t d_entry(const Aux &aux, const State &s, double pM3, double pI3, d
 // One round of the cross-lane max-plus scan: Al = A of lane - 2^r.
 template <class Aux>
 PF_HD double d_round(const Aux &aux, double A, double Al, int r) {
-    const double t0 = Al + aux(K_CWR + r);
+    const Pair w = aux.pair(K_CWR + (r & ~1));
+    const double t0 = Al + ((r & 1) ? w.b : w.a);
     return A >= t0 ? A : t0;
 }
 
@@ -200,9 +214,10 @@ PF_HD uint32_t d_final(const Aux &aux, State &s, const double a[P], double Din) 
     uint32_t bits = 0u;
     double D = Din;
     s.Dprev = Din;
+    const Pair h01 = aux.pair(K_WH), h23 = aux.pair(K_WH + 2);
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const double t0 = D + aux(K_WD + q * 3 + 2);
+        const double t0 = D + (q == 0 ? h01.a : (q == 1 ? h01.b : (q == 2 ? h23.a : h23.b)));
         if (a[q] >= t0) {
             D = a[q];
         } else {

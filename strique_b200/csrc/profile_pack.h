@@ -168,16 +168,22 @@ inline bool profile_pack(const strique_hmm_desc *d, ProfileImage *img, std::stri
     img->p_off = p_off;
     img->tab.assign((size_t)pf::K_TOTAL * 32, 0.0);
     auto T = [&](int k, int p) -> double & { return img->tab[(size_t)(k) * 32 + p / pf::P]; };
+    // table index of in-edge k of the M / I / D slot of in-lane position q (k as in struct Pos)
+    auto kM = [](int q, int k) {
+        return k == 3 ? pf::K_E2 + q * 2 : (k == 5 ? pf::K_WM2 + q : pf::K_WMR + q * 4 + (k == 4 ? 3 : k));
+    };
+    auto kI = [](int q, int k) { return k == 2 ? pf::K_E2 + q * 2 + 1 : pf::K_WI + q * 2 + k; };
+    auto kD = [](int q, int k) { return k == 2 ? pf::K_WH + q : pf::K_WD + q * 2 + k; };
     // defaults: every weight -inf, emissions 0
     for (int p = 0; p < pf::NPOS; ++p) {
         const int q = p % pf::P;
-        for (int k = 0; k < 6; ++k) T(pf::K_WM + q * 6 + k, p) = NINF;
-        for (int k = 0; k < 3; ++k) T(pf::K_WI + q * 3 + k, p) = NINF;
-        for (int k = 0; k < 3; ++k) T(pf::K_WD + q * 3 + k, p) = NINF;
+        for (int k = 0; k < 6; ++k) T(kM(q, k), p) = NINF;
+        for (int k = 0; k < 3; ++k) T(kI(q, k), p) = NINF;
+        for (int k = 0; k < 3; ++k) T(kD(q, k), p) = NINF;
     }
     for (int lane = 0; lane < 32; ++lane) {
-        img->tab[(size_t)pf::K_WXM * 32 + lane] = NINF;
-        img->tab[(size_t)pf::K_WXD * 32 + lane] = NINF;
+        img->tab[(size_t)pf::K_WX * 32 + lane] = NINF;
+        img->tab[(size_t)(pf::K_WX + 1) * 32 + lane] = NINF;
     }
     img->em_kind.assign(pf::NPOS * 2, 2);
     img->em_a.assign(pf::NPOS * 2, 0.0);
@@ -189,11 +195,11 @@ inline bool profile_pack(const strique_hmm_desc *d, ProfileImage *img, std::stri
     for (int hp = 0; hp < nph; ++hp) {
         const Pos &ps = pos[hp];
         const int p = hp + p_off, q = p % pf::P;
-        for (int k = 0; k < 6; ++k) T(pf::K_WM + q * 6 + k, p) = ps.wM[k];
-        for (int k = 0; k < 3; ++k) T(pf::K_WI + q * 3 + k, p) = ps.wI[k];
-        for (int k = 0; k < 3; ++k) T(pf::K_WD + q * 3 + k, p) = ps.wD[k];
-        if (ps.hasXM) T(pf::K_WXM, p) = ps.wXM;
-        if (ps.hasXD) T(pf::K_WXD, p) = ps.wXD;
+        for (int k = 0; k < 6; ++k) T(kM(q, k), p) = ps.wM[k];
+        for (int k = 0; k < 3; ++k) T(kI(q, k), p) = ps.wI[k];
+        for (int k = 0; k < 3; ++k) T(kD(q, k), p) = ps.wD[k];
+        if (ps.hasXM) T(pf::K_WX, p) = ps.wXM;
+        if (ps.hasXD) T(pf::K_WX + 1, p) = ps.wXD;
         for (int slot = 0; slot < 2; ++slot) {
             const int l = slot == 0 ? ps.m : ps.i;
             if (l < 0) continue;
@@ -206,9 +212,9 @@ inline bool profile_pack(const strique_hmm_desc *d, ProfileImage *img, std::stri
                 img->em_a[idx] = a;
                 img->em_b[idx] = -log(b * SQRT_2_PI);
                 img->em_c[idx] = b > 0 ? 1.0 / (2.0 * (b * b)) : 0.0;
-                T(pf::K_EMU + q, p) = img->em_a[idx];
-                T(pf::K_EC0 + q, p) = img->em_b[idx];
-                T(pf::K_EC2 + q, p) = img->em_c[idx];
+                T(pf::K_EM + q * 2, p) = img->em_a[idx];
+                T(pf::K_EC + q * 2, p) = img->em_b[idx];
+                T(pf::K_EM + q * 2 + 1, p) = img->em_c[idx];
             } else {
                 img->em_kind[idx] = 1;
                 img->em_a[idx] = a;
@@ -217,9 +223,9 @@ inline bool profile_pack(const strique_hmm_desc *d, ProfileImage *img, std::stri
                 lo = std::max(lo, a);
                 hi = std::min(hi, b);
                 if (slot == 0) {
-                    T(pf::K_EC0 + q, p) = img->em_c[idx];       // mu = 0, c2 = 0: c0 - (x*x)*0 = c0 exactly
+                    T(pf::K_EC + q * 2, p) = img->em_c[idx];    // mu = 0, c2 = 0: c0 - (x*x)*0 = c0 exactly
                 } else {
-                    T(pf::K_EI + q, p) = img->em_c[idx];
+                    T(pf::K_EC + q * 2 + 1, p) = img->em_c[idx];
                 }
             }
         }
@@ -235,8 +241,8 @@ inline bool profile_pack(const strique_hmm_desc *d, ProfileImage *img, std::stri
     // ---- summed hop weights of the cross-lane scan (same association as the kernel's recurrence) --------
     double W[32];
     for (int lane = 0; lane < 32; ++lane) {
-        W[lane] = img->tab[(size_t)(pf::K_WD + 2) * 32 + lane];
-        for (int q = 1; q < pf::P; ++q) W[lane] += img->tab[(size_t)(pf::K_WD + q * 3 + 2) * 32 + lane];
+        W[lane] = img->tab[(size_t)pf::K_WH * 32 + lane];
+        for (int q = 1; q < pf::P; ++q) W[lane] += img->tab[(size_t)(pf::K_WH + q) * 32 + lane];
     }
     for (int r = 0; r < 5; ++r) {
         const int off = 1 << r;

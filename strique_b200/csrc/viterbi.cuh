@@ -106,19 +106,24 @@ struct VitFastBatch {
 };
 
 
+struct VitProfQueue {              // sequences of one model: order[begin, end), longest first
+    int32_t begin, end;
+};
+
 struct VitProfBatch {
     const double *x;
     const int64_t *x_off;
-    const int32_t *order;          // [n_seq] sequence ids, longest first
-    const int32_t *seq_model;      // [all sequences] model index of a sequence id
-    int n_seq;
+    const int32_t *order;          // sequence ids, grouped by model (queues), longest first inside a group
+    int n_models;
     const VitProfModelDev *models; // device array indexed by model
+    const VitProfQueue *queues;    // [n_models]
+    int *counters;                 // [n_models] sequences handed out so far (zeroed by the caller)
+    const int32_t *cta_model;      // [grid] first model of every CTA
     uint32_t *bp;
     const int64_t *bp_off;         // [all sequences] offset in 32-bit words (per sequence: (T+1) * 32 words)
     VitResult *res;
     uint8_t *pattern;
     uint16_t *path;
-    int *queue;
 };
 
 struct VitBatch {
@@ -141,7 +146,8 @@ int viterbi_fast_launch(strique_ctx *ctx, const VitFastShape &shape, const VitFa
 int viterbi_fast_teams(const VitFastShape &shape);   // sequences per CTA task
 // profile kernel: packs the model if its layout hints describe a linear profile (sets m->has_profile), launch
 int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
-int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b);
+int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta);
+int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b, int grid);
 // decodes sequences of several models in one pass: seq_model[s] indexes ctx->models
 int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
                              int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,

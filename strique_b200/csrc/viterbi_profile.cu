@@ -10,14 +10,17 @@
 //   * every regular edge reads a register of the same lane or one of three values shuffled up from
 //     lane l-1 -- no shared-memory value columns, no barriers;
 //   * the repeat loop (d2 -> M_0, d1 -> s1) is one indexed shuffle pair;
-//   * in-edge weights of the emitting states live in registers, the delete-chain / emission constants in a
-//     per-warp shared-memory table read with conflict-free LDS.64 [lane*8 + const];
+//   * the four hottest in-edge weights of every match state live in registers, the other per-position
+//     constants in a shared-memory table of the CTA's current model, laid out in (even, odd) pairs and read
+//     with conflict-free LDS.128 [lane*16 + const] -- 128 registers per thread, 16 warps per SM;
 //   * the delete chain of a column is a max-plus scan: sequential inside the lane, Kogge-Stone across
 //     lanes; the E1 part of the NEXT column (all edges from emitting states) sits in the same basic
 //     block and fills the shuffle / fp64 latencies of the scan;
 //   * back-pointers: one byte per position -> ONE 32-bit word per lane per column = 128 B per time step,
 //     coalesced; traceback by the same warp over rows staged 32 at a time with cp.async.
-// Warps are independent: each pulls sequences (longest first) from a global queue.
+// A CTA (4 independent warps, no barrier inside a sequence) serves one model at a time: its warps pull
+// sequences (longest first) from that model's queue; when the queue runs dry the CTA moves on to the next
+// model that still has work (one barrier + table reload), so both strands / all loci share one launch.
 #include <math.h>
 
 #include <algorithm>
@@ -30,15 +33,18 @@ namespace strique {
 namespace {
 
 constexpr int PROF_WARPS = 4;                       // warps per CTA
+constexpr int PROF_CTAS_PER_SM = 4;
 constexpr int PROF_STAGE_ROWS = 32;
-constexpr int PROF_AUX_BYTES = pf::K_NAUX * 32 * 8;
-constexpr int PROF_STAGE_BYTES = PROF_STAGE_ROWS * 32 * 4;
-constexpr int PROF_WARP_BYTES = PROF_AUX_BYTES + PROF_STAGE_BYTES;
+constexpr int PROF_AUX_BYTES = pf::K_NAUX * 32 * 8; // table of the CTA's current model (shared by its warps)
+constexpr int PROF_STAGE_BYTES = PROF_STAGE_ROWS * 32 * 4;   // per warp: back-pointer rows of the traceback
 static_assert(PROF_STAGE_BYTES >= 3 * pf::NPOS * 8, "the END gather reuses the stage area");
 
-struct AuxShared {                                  // tab(k) of this lane, k >= K_NREG
-    const double *base;                             // &aux[lane]
-    __device__ __forceinline__ double operator()(int k) const { return base[(k - pf::K_NREG) * 32]; }
+struct AuxShared {                                  // entries k >= K_NREG of this lane, pair-interleaved
+    const double2 *base;                            // &aux[lane]; pair j of lane l at aux[j * 32 + l]
+    __device__ __forceinline__ pf::Pair pair(int k) const {
+        const double2 v = base[((k - pf::K_NREG) >> 1) * 32];
+        return pf::Pair{v.x, v.y};
+    }
 };
 struct TabGlobal {
     const double *base;                             // &tab[lane]
@@ -49,46 +55,41 @@ __device__ __forceinline__ double pick4(const double v[pf::P], int q) {
     return q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : v[3]));
 }
 
-__global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(VitProfBatch b) {
+__global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_profile_kernel(VitProfBatch b) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next_model;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wbase = smem + (size_t)warp * PROF_WARP_BYTES;
-    double *aux_s = reinterpret_cast<double *>(wbase);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + PROF_AUX_BYTES);
-    const AuxShared aux{aux_s + lane};
+    double *aux_s = reinterpret_cast<double *>(smem);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + PROF_AUX_BYTES + (size_t)warp * PROF_STAGE_BYTES);
+    const AuxShared aux{reinterpret_cast<const double2 *>(smem) + lane};
     const double NINF = pf::ninf();
     const unsigned FULL = 0xffffffffu;
 
+    int model = b.cta_model[blockIdx.x];
+  for (;;) {                                            // ---- one model of this CTA -----------------------
+    const VitProfModelDev &m = b.models[model];
+    const VitProfQueue mq = b.queues[model];
+    // table of the model: logical [k][lane] in global memory -> pair-interleaved in shared memory
+    for (int i = threadIdx.x; i < pf::K_NAUX * 32; i += PROF_WARPS * 32) {
+        const int k = i >> 5, l = i & 31;
+        aux_s[((k >> 1) * 32 + l) * 2 + (k & 1)] = __ldg(m.tab + (pf::K_NREG + k) * 32 + l);
+    }
     pf::Regs R;
-    int cur_model = -1;
+    pf::load_regs(TabGlobal{m.tab + lane}, R);
     // warp-uniform model scalars
-    int p_start = 0, xlane = 0, xq = 0, xm_slot = 0, xd_slot = 0;
-    double lo = 0.0, hi = 0.0;
+    const int p_start = m.p_start;
+    const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+    const int xlane = xp / pf::P, xq = xp % pf::P;
+    const int xm_slot = m.trace.xm_src_slot, xd_slot = m.trace.xd_src_slot;
+    const double lo = m.lo, hi = m.hi;
+    __syncthreads();
 
-    for (;;) {
+    for (;;) {                                          // ---- one sequence of this warp -------------------
         int task = 0;
-        if (lane == 0) task = atomicAdd(b.queue, 1);
+        if (lane == 0) task = mq.begin + atomicAdd(b.counters + model, 1);
         task = __shfl_sync(FULL, task, 0);
-        if (task >= b.n_seq) break;
+        if (task >= mq.end) break;
         const int seq = b.order[task];
-        const int mi = b.seq_model[seq];
-        const VitProfModelDev &m = b.models[mi];
-        if (mi != cur_model) {
-            cur_model = mi;
-            __syncwarp();
-#pragma unroll 1
-            for (int k = 0; k < pf::K_NAUX; ++k) aux_s[k * 32 + lane] = __ldg(m.tab + (pf::K_NREG + k) * 32 + lane);
-            pf::load_regs(TabGlobal{m.tab + lane}, R);
-            p_start = m.p_start;
-            const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
-            xlane = xp / pf::P;
-            xq = xp % pf::P;
-            xm_slot = m.trace.xm_src_slot;
-            xd_slot = m.trace.xd_src_slot;
-            lo = m.lo;
-            hi = m.hi;
-            __syncwarp();
-        }
         const int64_t xo = b.x_off[seq];
         const int T = (int)(b.x_off[seq + 1] - xo);
         const double *x = b.x + xo;
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(Vit
             const double vm = pick4(S.M, xq), vi = pick4(S.I, xq);
             const double xm = __shfl_sync(FULL, xm_slot ? vi : vm, xlane);
             const double xd = __shfl_sync(FULL, xd_slot ? vi : vm, xlane);
-            pf::e1(R, S, pM3, pI3, pM2, xm);
+            pf::e1(R, aux, S, pM3, pI3, pM2, xm);
             double a[pf::P], A;
             uint32_t bits = pf::d_entry(aux, S, pM3, pI3, xd, a, A);
 #pragma unroll
@@ -130,9 +131,8 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(Vit
         for (int t = 1; t <= T; ++t) {
             const double xnext = t < T ? __ldg(x + t) : 0.0;
             double eM[pf::P], eI[pf::P];
-            if (xcur >= lo && xcur <= hi) {
-                pf::emissions_fast(aux, xcur, eM, eI);
-            } else {                                         // outside a Uniform range or NaN: general form
+            pf::emissions_fast(aux, xcur, eM, eI);
+            if (!(xcur >= lo && xcur <= hi)) {               // outside a Uniform range or NaN: general form (rare)
 #pragma unroll
                 for (int q = 0; q < pf::P; ++q) {
                     const int i0 = (lane * pf::P + q) * 2;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(Vit
                     eI[q] = pf::emission_slow(m.em_kind[i0 + 1], m.em_a[i0 + 1], m.em_b[i0 + 1], m.em_c[i0 + 1], xcur);
                 }
             }
-            const uint32_t word = pf::e2_emit(R, S, eM, eI);
+            const uint32_t word = pf::e2_emit(aux, S, eM, eI);
             const uint32_t dbits = block();
             bp[(size_t)t * 32 + lane] = word | dbits;
             xcur = xnext;
@@ -228,21 +228,42 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, 3) viterbi_profile_kernel(Vit
         if (lane == 0) b.res[seq] = r;
         __syncwarp();
     }
+    // ---- this model's queue is dry: move the CTA to the next model that still has sequences --------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int next = -1;
+        for (int i = 1; i < b.n_models && next < 0; ++i) {
+            const int mm = (model + i) % b.n_models;
+            const VitProfQueue q = b.queues[mm];
+            if (q.end > q.begin && *((volatile int *)b.counters + mm) < q.end - q.begin) next = mm;
+        }
+        s_next_model = next;
+    }
+    __syncthreads();
+    model = s_next_model;
+    if (model < 0) return;
+  }
 }
 
 }  // namespace
 
-int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b) {
-    if (b.n_seq == 0) return STRIQUE_OK;
-    const size_t smem = (size_t)PROF_WARPS * PROF_WARP_BYTES;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(viterbi_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+size_t viterbi_profile_smem_bytes() { return (size_t)PROF_AUX_BYTES + (size_t)PROF_WARPS * PROF_STAGE_BYTES; }
+
+// Largest useful grid: every resident CTA slot of the device (persistent CTAs pulling from the queues).
+int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta) {
+    const size_t smem = viterbi_profile_smem_bytes();
+    if (cudaFuncSetAttribute(viterbi_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_kernel, PROF_WARPS * 32, smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_kernel, PROF_WARPS * 32, smem) != cudaSuccess) return 0;
     if (per_sm < 1) per_sm = 1;
-    int grid = ctx->num_sms * per_sm;
-    const int need = (b.n_seq + PROF_WARPS - 1) / PROF_WARPS;
-    if (grid > need) grid = need;
-    viterbi_profile_kernel<<<grid, PROF_WARPS * 32, smem, ctx->stream>>>(b);
+    if (warps_per_cta) *warps_per_cta = PROF_WARPS;
+    return ctx->num_sms * per_sm;
+}
+
+// grid CTAs; b.cta_model[0..grid) names the first model of every CTA
+int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b, int grid) {
+    if (grid <= 0) return STRIQUE_OK;
+    viterbi_profile_kernel<<<grid, PROF_WARPS * 32, viterbi_profile_smem_bytes(), ctx->stream>>>(b);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return STRIQUE_OK;

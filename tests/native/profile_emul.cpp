@@ -19,6 +19,7 @@ struct TabLane {
     const double *tab;
     int lane;
     double operator()(int k) const { return tab[(size_t)k * 32 + lane]; }
+    pf::Pair pair(int k) const { return pf::Pair{(*this)(k), (*this)(k + 1)}; }
 };
 }  // namespace
 
@@ -62,7 +63,7 @@ extern "C" int strique_test_profile_emulate(const strique_hmm_desc *d, const dou
             pM3[l] = st[s].M[3]; pI3[l] = st[s].I[3]; pM2[l] = st[s].M[2];
         }
         for (int l = 0; l < 32; ++l) {
-            pf::e1(regs[l], st[l], pM3[l], pI3[l], pM2[l], xm);
+            pf::e1(regs[l], aux[l], st[l], pM3[l], pI3[l], pM2[l], xm);
             dbits[l] = pf::d_entry(aux[l], st[l], pM3[l], pI3[l], xd, a[l], A[l]);
         }
         for (int r = 0; r < 5; ++r) {
@@ -92,7 +93,7 @@ extern "C" int strique_test_profile_emulate(const strique_hmm_desc *d, const dou
                     eI[q] = pf::emission_slow(img.em_kind[i0 + 1], img.em_a[i0 + 1], img.em_b[i0 + 1], img.em_c[i0 + 1], xt);
                 }
             }
-            word[l] = pf::e2_emit(regs[l], st[l], eM, eI);
+            word[l] = pf::e2_emit(aux[l], st[l], eM, eI);
         }
         block(dbits);
         for (int l = 0; l < 32; ++l) bp[(size_t)t * 32 + l] = word[l] | dbits[l];

@@ -138,7 +138,12 @@ def test_profile_team_and_generic_kernels_agree(ctx, model_file, mod_model_file,
                     continue
                 # exact ties (sequences too short to traverse the model, NaN samples that score log 1 in
                 # every state) are broken by candidate order, which the profile kernel does not share
-                degenerate = vi == 1 and (len(segs[k]) < 100 or np.isnan(segs[k]).any())
+                # ... and so are samples outside every uniform range: only match states can emit them, the
+                # path is forced along the delete chains, and flank positions with identical k-mers then tie
+                # to the last ulp (hop weights summed in a different association) -- equal log p, asserted
+                # above, is all that can be asked of either decoder there
+                forced = bool((segs[k] > 500).any())
+                degenerate = forced or (vi == 1 and (len(segs[k]) < 100 or np.isnan(segs[k]).any()))
                 if degenerate and not np.array_equal(path1[k], path0[k]):
                     continue
                 assert np.array_equal(path1[k], path0[k]), (vi, k)
