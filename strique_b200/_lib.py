@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libstrique_b200.so')
+# STRIQUE_LIB: another build of the same library (kernel A/B experiments, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get('STRIQUE_LIB') or os.path.join(_HERE, 'libstrique_b200.so')
 
 HOST, DEVICE = 0, 1
 

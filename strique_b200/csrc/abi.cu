@@ -156,7 +156,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::max<size_t>((size_t)1 << 30, (size_t)(free_b * 0.6));
-    const int trace_warps = ctx->num_sms * 8;
+    const int trace_warps = ctx->num_sms * (getenv("STRIQUE_TRACE_WARPS") ? atoi(getenv("STRIQUE_TRACE_WARPS")) : 8);
     const int fix_cap = 1 << 16;
 
     TRY(d_col0.ensure(ctx, col0.size() * sizeof(float)));

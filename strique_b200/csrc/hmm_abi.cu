@@ -222,65 +222,42 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
             CUDA_TRY(ctx, cudaMemcpyAsync(d_bpoff.p, bpoff.data(), (size_t)n_seq * 8, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
             if (g.profile) {
-                // one warp per sequence; a queue per model (longest first), CTAs dealt to the models in
-                // proportion to their time steps -- models of all loci / strands in one launch
-                DevBuf &d_pmodels = ctx->buf("vit.prof_models"), &d_pq = ctx->buf("vit.prof_queues"),
-                       &d_cta = ctx->buf("vit.prof_cta_model");
+                // one warp per sequence.  CTA task = up to warps_per_cta sequences of ONE model that are neighbours
+                // in its length order (they finish together, so the CTA barrier between tasks costs nothing); one
+                // queue over the tasks of all models (loci / strands), longest first: every hand-out is a whole CTA
+                // and no warp ever waits for a sequence of another warp's model.
+                DevBuf &d_pmodels = ctx->buf("vit.prof_models");
                 std::vector<VitProfModelDev> pm(n_models);
                 for (int i = 0; i < n_models; ++i)
                     if (ctx->models[i]->has_profile) pm[i] = ctx->models[i]->profile; else memset(&pm[i], 0, sizeof(pm[i]));
                 std::vector<std::vector<int32_t>> per_model(n_models);
-                std::vector<double> steps(n_models, 0.0);
-                for (size_t i = i0; i < i1; ++i) {
-                    per_model[seq_model[g.ids[i]]].push_back(g.ids[i]);       // keeps the length order
-                    steps[seq_model[g.ids[i]]] += (double)len(g.ids[i]) + 64.0;
-                }
-                std::vector<int32_t> order;
-                std::vector<VitProfQueue> queues(n_models);
-                for (int mi = 0; mi < n_models; ++mi) {
-                    queues[mi].begin = (int32_t)order.size();
-                    order.insert(order.end(), per_model[mi].begin(), per_model[mi].end());
-                    queues[mi].end = (int32_t)order.size();
-                }
+                for (size_t i = i0; i < i1; ++i) per_model[seq_model[g.ids[i]]].push_back(g.ids[i]);   // keeps the length order
                 int warps_per_cta = 1;
                 int grid = viterbi_profile_max_grid(ctx, &warps_per_cta);
                 if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi_profile_kernel: occupancy query failed");
-                grid = std::min(grid, (n + warps_per_cta - 1) / warps_per_cta + n_models);
-                // CTA -> first model: largest-remainder apportionment of the CTAs over the models with work,
-                // at least one CTA each; interleaved so that the CTAs of one SM spread over the models
-                std::vector<int32_t> cta_model;
-                {
-                    double all = 0.0;
-                    int with_work = 0;
-                    for (int mi = 0; mi < n_models; ++mi) if (!per_model[mi].empty()) { all += steps[mi]; ++with_work; }
-                    grid = std::max(grid, with_work);
-                    std::vector<int> share(n_models, 0);
-                    int dealt = 0;
-                    for (int mi = 0; mi < n_models; ++mi)
-                        if (!per_model[mi].empty()) {
-                            share[mi] = std::max(1, (int)(steps[mi] / all * (grid - with_work)) + 1);
-                            share[mi] = std::min<int>(share[mi], (int)((per_model[mi].size() + warps_per_cta - 1) / warps_per_cta));
-                            dealt += share[mi];
-                        }
-                    grid = dealt;
-                    std::vector<int> left = share;
-                    while ((int)cta_model.size() < grid)
-                        for (int mi = 0; mi < n_models; ++mi)
-                            if (left[mi] > 0) { cta_model.push_back(mi); --left[mi]; }
+                struct HostTask { int model; size_t first; int count; int64_t maxlen; };
+                std::vector<HostTask> tasks;
+                for (int mi = 0; mi < n_models; ++mi)
+                    for (size_t k = 0; k < per_model[mi].size(); k += warps_per_cta)
+                        tasks.push_back(HostTask{mi, k, (int)std::min<size_t>(warps_per_cta, per_model[mi].size() - k),
+                                                 len(per_model[mi][k])});
+                std::stable_sort(tasks.begin(), tasks.end(), [](const HostTask &a, const HostTask &b) { return a.maxlen > b.maxlen; });
+                std::vector<int32_t> order;
+                std::vector<VitCtaTask> ctas;
+                for (const HostTask &t : tasks) {
+                    ctas.push_back(VitCtaTask{t.model, (int32_t)order.size(), t.count});
+                    order.insert(order.end(), per_model[t.model].begin() + t.first, per_model[t.model].begin() + t.first + t.count);
                 }
+                grid = std::min<int>(grid, (int)ctas.size());
                 TRY(d_pmodels.ensure(ctx, (size_t)n_models * sizeof(VitProfModelDev)));
-                TRY(d_pq.ensure(ctx, (size_t)n_models * sizeof(VitProfQueue)));
-                TRY(d_cta.ensure(ctx, cta_model.size() * 4));
-                TRY(d_queue.ensure(ctx, std::max<size_t>(64, (size_t)n_models * 4)));
-                CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, std::max<size_t>(64, (size_t)n_models * 4), ctx->stream));
+                TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_pmodels.p, pm.data(), pm.size() * sizeof(VitProfModelDev), cudaMemcpyHostToDevice, ctx->stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_pq.p, queues.data(), queues.size() * sizeof(VitProfQueue), cudaMemcpyHostToDevice, ctx->stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_cta.p, cta_model.data(), cta_model.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
                 VitProfBatch b;
                 b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
                 b.n_models = n_models; b.models = d_pmodels.as<VitProfModelDev>();
-                b.queues = d_pq.as<VitProfQueue>(); b.counters = d_queue.as<int>(); b.cta_model = d_cta.as<int32_t>();
+                b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size(); b.counters = d_queue.as<int>();
                 b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
                 b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
                 TRY(viterbi_profile_launch(ctx, b, grid));

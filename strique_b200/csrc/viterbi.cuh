@@ -106,19 +106,16 @@ struct VitFastBatch {
 };
 
 
-struct VitProfQueue {              // sequences of one model: order[begin, end), longest first
-    int32_t begin, end;
-};
 
 struct VitProfBatch {
     const double *x;
     const int64_t *x_off;
-    const int32_t *order;          // sequence ids, grouped by model (queues), longest first inside a group
+    const int32_t *order;          // sequence ids, the sequences of a CTA task are consecutive
     int n_models;
     const VitProfModelDev *models; // device array indexed by model
-    const VitProfQueue *queues;    // [n_models]
-    int *counters;                 // [n_models] sequences handed out so far (zeroed by the caller)
-    const int32_t *cta_model;      // [grid] first model of every CTA
+    const VitCtaTask *tasks;       // [n_tasks] <= 4 sequences of one model with similar lengths; longest task first
+    int n_tasks;
+    int *counters;                 // [0]: CTA tasks handed out so far (zeroed by the caller)
     uint32_t *bp;
     const int64_t *bp_off;         // [all sequences] offset in 32-bit words (per sequence: (T+1) * 32 words)
     VitResult *res;

@@ -57,7 +57,7 @@ __device__ __forceinline__ double pick4(const double v[pf::P], int q) {
 
 __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_profile_kernel(VitProfBatch b) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_next_model;
+    __shared__ int s_task;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *aux_s = reinterpret_cast<double *>(smem);
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem + PROF_AUX_BYTES + (size_t)warp * PROF_STAGE_BYTES);
@@ -65,30 +65,36 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_pro
     const double NINF = pf::ninf();
     const unsigned FULL = 0xffffffffu;
 
-    int model = b.cta_model[blockIdx.x];
-  for (;;) {                                            // ---- one model of this CTA -----------------------
-    const VitProfModelDev &m = b.models[model];
-    const VitProfQueue mq = b.queues[model];
-    // table of the model: logical [k][lane] in global memory -> pair-interleaved in shared memory
-    for (int i = threadIdx.x; i < pf::K_NAUX * 32; i += PROF_WARPS * 32) {
-        const int k = i >> 5, l = i & 31;
-        aux_s[((k >> 1) * 32 + l) * 2 + (k & 1)] = __ldg(m.tab + (pf::K_NREG + k) * 32 + l);
-    }
+    int model = -1;
     pf::Regs R;
-    pf::load_regs(TabGlobal{m.tab + lane}, R);
-    // warp-uniform model scalars
-    const int p_start = m.p_start;
-    const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
-    const int xlane = xp / pf::P, xq = xp % pf::P;
-    const int xm_slot = m.trace.xm_src_slot, xd_slot = m.trace.xd_src_slot;
-    const double lo = m.lo, hi = m.hi;
+    int p_start = 0, xlane = 0, xq = 0, xm_slot = 0, xd_slot = 0;
+    double lo = 0.0, hi = 0.0;
+  for (;;) {                                            // ---- one CTA task: <= PROF_WARPS sequences of one model ----
+    __syncthreads();                                    // everybody is done with s_task and the table
+    if (threadIdx.x == 0) s_task = atomicAdd(b.counters, 1);
     __syncthreads();
+    if (s_task >= b.n_tasks) return;
+    const VitCtaTask ct = b.tasks[s_task];
+    const VitProfModelDev &m = b.models[ct.model];
+    if (ct.model != model) {
+        model = ct.model;
+        // table of the model: logical [k][lane] in global memory -> pair-interleaved in shared memory
+        for (int i = threadIdx.x; i < pf::K_NAUX * 32; i += PROF_WARPS * 32) {
+            const int k = i >> 5, l = i & 31;
+            aux_s[((k >> 1) * 32 + l) * 2 + (k & 1)] = __ldg(m.tab + (pf::K_NREG + k) * 32 + l);
+        }
+        pf::load_regs(TabGlobal{m.tab + lane}, R);
+        // warp-uniform model scalars
+        p_start = m.p_start;
+        const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+        xlane = xp / pf::P; xq = xp % pf::P;
+        xm_slot = m.trace.xm_src_slot; xd_slot = m.trace.xd_src_slot;
+        lo = m.lo; hi = m.hi;
+        __syncthreads();
+    }
 
-    for (;;) {                                          // ---- one sequence of this warp -------------------
-        int task = 0;
-        if (lane == 0) task = mq.begin + atomicAdd(b.counters + model, 1);
-        task = __shfl_sync(FULL, task, 0);
-        if (task >= mq.end) break;
+    if (warp < ct.count) {                              // ---- one sequence of this warp -------------------
+        const int task = ct.first + warp;
         const int seq = b.order[task];
         const int64_t xo = b.x_off[seq];
         const int T = (int)(b.x_off[seq + 1] - xo);
@@ -205,21 +211,39 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_pro
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     __syncwarp();
                 }
-                if (slot < 2) {
-                    if (t < 1) { r.status = 2; break; }
-                    const int idx = p * 2 + slot;
-                    const unsigned fl = m.flags[idx];
-                    if (fl & HMM_FLAG_COUNT) ++r.n_count;
-                    if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - 1; }
-                    if (fl & HMM_FLAG_SEP) {
-                        if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; in_group = false; }
-                    } else {
-                        in_group = true;
-                        last_mod = (fl & HMM_FLAG_MOD) ? '1' : '0';
-                    }
-                    if (path && lane == 0) path[t - 1] = (uint16_t)m.state_id[idx];
+                if (slot == 2) {                  // silent delete state: same column
+                    pf::back(stage[(t - stage_lo) * 32 + (p >> 2)], tc, p, slot, t);
+                    continue;
                 }
-                pf::back(stage[(t - stage_lo) * 32 + (p >> 2)], tc, p, slot, t);
+                if (t < 1) { r.status = 2; break; }
+                // Emitting state (p, slot) at column t.  Samples dwell in a state, so most pointers are self loops:
+                // lane i looks at column t - i, the warp skips the whole run of self loops at once and then takes
+                // the first other pointer (all lanes keep the same cursor; lane 0 / lane i write the outputs).
+                const int ti = t - lane;
+                const bool valid = ti >= stage_lo && ti >= 1;
+                const uint32_t wfull = valid ? stage[(ti - stage_lo) * 32 + (p >> 2)] : 0u;
+                const uint32_t f = wfull >> (8 * (p & 3));
+                const bool self = valid && (slot == 0 ? (f & 0xfu) == 0u : (f & 0x30u) == 0u);
+                const unsigned other = ~__ballot_sync(FULL, self);
+                const int k = other ? __ffs(other) - 1 : 32;               // columns t .. t-k+1 are self loops
+                const bool step = k < 32 && ((__ballot_sync(FULL, valid) >> k) & 1u);   // column t-k is staged
+                const int visits = k + (step ? 1 : 0);                     // >= 1: column t itself is staged
+                const int idx = p * 2 + slot;
+                const unsigned fl = m.flags[idx];
+                if (fl & HMM_FLAG_COUNT) r.n_count += visits;
+                if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - visits; }
+                if (fl & HMM_FLAG_SEP) {
+                    if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; in_group = false; }
+                } else {
+                    in_group = true;
+                    last_mod = (fl & HMM_FLAG_MOD) ? '1' : '0';
+                }
+                if (path && lane < visits) path[t - 1 - lane] = (uint16_t)m.state_id[idx];
+                t -= k;
+                if (step) {
+                    const uint32_t w = __shfl_sync(FULL, wfull, k);
+                    pf::back(w, tc, p, slot, t);
+                }
             }
             if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; }
             if (r.status == 0 && t != 0) r.status = 2;
@@ -228,20 +252,6 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_pro
         if (lane == 0) b.res[seq] = r;
         __syncwarp();
     }
-    // ---- this model's queue is dry: move the CTA to the next model that still has sequences --------------
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int next = -1;
-        for (int i = 1; i < b.n_models && next < 0; ++i) {
-            const int mm = (model + i) % b.n_models;
-            const VitProfQueue q = b.queues[mm];
-            if (q.end > q.begin && *((volatile int *)b.counters + mm) < q.end - q.begin) next = mm;
-        }
-        s_next_model = next;
-    }
-    __syncthreads();
-    model = s_next_model;
-    if (model < 0) return;
   }
 }
 
@@ -260,7 +270,7 @@ int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta) {
     return ctx->num_sms * per_sm;
 }
 
-// grid CTAs; b.cta_model[0..grid) names the first model of every CTA
+// grid persistent CTAs pulling CTA tasks from the queue
 int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b, int grid) {
     if (grid <= 0) return STRIQUE_OK;
     viterbi_profile_kernel<<<grid, PROF_WARPS * 32, viterbi_profile_smem_bytes(), ctx->stream>>>(b);
