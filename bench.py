@@ -42,20 +42,56 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('STRIQUE_BENCH_BATCH', 4096)),
-                    help='reads per step and per GPU')
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS),
+                    help='BASELINE.json configuration: c2 (default, the one the metric is quoted on), c3 methylation, '
+                         'c4 four-locus panel, c5 long expansions')
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('STRIQUE_BENCH_BATCH', 0)),
+                    help='reads per step and per GPU (0: the default of the workload)')
     ap.add_argument('--n-lo', type=int, default=2)
     ap.add_argument('--n-hi', type=int, default=1000)
-    ap.add_argument('--mod', action='store_true', help='configuration C3: also run the methylation HMM')
+    ap.add_argument('--mod', action='store_true', help='same as --workload c3')
     ap.add_argument('--cpu-reads', type=int, default=0, help='reads of the CPU baseline sample (0: one per core, <= 32)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.mod and args.workload == 'c2':
+        args.workload = 'c3'
+    w = WORKLOADS[args.workload]
+    args.mod = w['mod']
+    args.loci = w['loci']
+    args.fixed_n = w['fixed_n']
+    if not args.batch:
+        args.batch = w['batch']
+    return args
+
+
+# BASELINE.json configs[1..4]; batch = default reads per step and per GPU
+WORKLOADS = {
+    'c2': dict(loci=('c9orf72',), mod=False, fixed_n=None, batch=8192),
+    'c3': dict(loci=('c9orf72',), mod=True, fixed_n=None, batch=8192),
+    'c4': dict(loci=('c9orf72', 'fmr1', 'atxn10', 'dmpk'), mod=False, fixed_n=None, batch=8192),
+    'c5': dict(loci=('c9orf72',), mod=False, fixed_n=4000, batch=2048, flank=4000),
+}
 
 
 def workload_name(args):
-    return ('C%d: synthetic c9orf72 GGCCCC reads, n~U{%d..%d}, r9_4_450bps%s, noisy int16, strands 50/50, '
-            '%d reads per step per GPU' % (3 if args.mod else 2, args.n_lo, args.n_hi,
-                                           ' + mCpG methylation HMM' if args.mod else '', args.batch))
+    from strique_b200.workload import LOCI
+    loci = ' / '.join('%s %s' % (name, LOCI[name][0]) for name in args.loci)
+    n = 'n=%d' % args.fixed_n if args.fixed_n else 'n~U{%d..%d}' % (args.n_lo, args.n_hi)
+    return ('%s: synthetic %s reads, %s, r9_4_450bps%s, noisy int16, strands 50/50, %d reads per step per GPU'
+            % (args.workload.upper(), loci, n, ' + mCpG methylation HMM' if args.mod else '', args.batch))
+
+
+def make_workload(args, pm, pm_mod, n_reads, seed):
+    from strique_b200 import workload
+    return workload.make_reads(pm, n_reads, seed=seed, loci=args.loci, n_lo=args.n_lo, n_hi=args.n_hi,
+                               pm_mod=pm_mod if args.mod else None, mod_fraction=0.5 if args.mod else 0.0,
+                               fixed_n=args.fixed_n, flank=WORKLOADS[args.workload].get('flank', 1000))
+
+
+def flank_cells(items):
+    """DP cells of the two flank alignments of every (target, signal, strand) item."""
+    from strique_b200.workload import LOCI
+    return sum(len(s) * 6 * ((len(LOCI[name][1]) - 5) + (len(LOCI[name][2]) - 5)) for name, s, _ in items)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -110,12 +146,13 @@ class ClockSampler(threading.Thread):
 _cpu_counter = None
 
 
-def _cpu_init(use_mod):
+def _cpu_init(use_mod, loci):
     global _cpu_counter
     from oracle import reference_path as rp
     from strique_b200.workload import LOCI
     _cpu_counter = rp.RefRepeatCounter(MODEL, mod_model_file=MOD_MODEL if use_mod else None)
-    _cpu_counter.add_target('c9orf72', *LOCI['c9orf72'])
+    for name in loci:
+        _cpu_counter.add_target(name, *LOCI[name])
 
 
 def _cpu_detect(item):
@@ -134,12 +171,12 @@ class CpuPool(object):
     """Pool of worker processes running the CPU path (the reference's mt_dispatcher pattern,
     scripts/STRique.py:733-830); the HMMs are built in every worker before timing (S.py:682)."""
 
-    def __init__(self, cores, use_mod, warm_item):
+    def __init__(self, cores, use_mod, warm_item, loci=('c9orf72',)):
         import multiprocessing as mp
         import subprocess
         subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'liboracle.so'])
         self.cores = cores
-        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init, initargs=(use_mod,))
+        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init, initargs=(use_mod, tuple(loci)))
         self.pool.map(_cpu_detect, [warm_item] * cores, chunksize=1)
 
     def run(self, items):
@@ -160,12 +197,10 @@ def reference_main(args, rank, world):
     cores = os.cpu_count() or 1
     pm = pmod.pore_model(MODEL)
     n_sample = args.cpu_reads or min(cores, 256)
-    pool_reads = workload.make_reads(pm, n_sample, seed=0, n_lo=args.n_lo, n_hi=args.n_hi,
-                                     pm_mod=pmod.pore_model(MOD_MODEL) if args.mod else None,
-                                     mod_fraction=0.5 if args.mod else 0.0)
+    pool_reads = make_workload(args, pm, pmod.pore_model(MOD_MODEL) if args.mod else None, n_sample, seed=0)
     items = [(n, s, st) for n, s, st, _ in pool_reads]
     times = []
-    pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])))
+    pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])), args.loci)
     for step in range(args.warmup + args.steps):
         wall, _ = pool.run(items)
         if step >= args.warmup:
@@ -173,7 +208,7 @@ def reference_main(args, rank, world):
     pool.close()
     total = sum(times)
     value = n_sample * len(times) / total
-    cells = sum(2 * len(s) * 870 for _, s, _ in items)
+    cells = flank_cells(items)
     line = {'impl': 'reference', 'metric': 'reads/s', 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 align / f64 viterbi',
@@ -210,13 +245,13 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ctx = _lib.Context(local_rank)
     dt = repeatCounter(MODEL, mod_model_file=MOD_MODEL if args.mod else None, context=ctx)
-    dt.add_target('c9orf72', *workload.LOCI['c9orf72'])
+    for name in args.loci:
+        dt.add_target(name, *workload.LOCI[name])
     cfg = dt._detect_config()
 
     # ---- this rank's batch ------------------------------------------------------------------------
     t_gen = time.time()
-    reads = workload.make_reads(dt.pm, args.batch, seed=1000 + rank, n_lo=args.n_lo, n_hi=args.n_hi,
-                                pm_mod=dt.pm_mod if args.mod else None, mod_fraction=0.5 if args.mod else 0.0)
+    reads = make_workload(args, dt.pm, dt.pm_mod, args.batch, seed=1000 + rank)
     tids = np.array([dt._target_id(name, strand) for name, _, strand, _ in reads], dtype=np.int32)
     raw_np, off, kind = _lib.Context._pack_raw([s for _, s, _, _ in reads])
     t_gen = time.time() - t_gen
@@ -348,7 +383,7 @@ def main():
             cores = os.cpu_count() or 1
             n_sample = args.cpu_reads or min(cores, 32)
             items = [(n, s, st) for n, s, st, _ in reads[:n_sample]]
-            pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])))
+            pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])), args.loci)
             wall, cpu_res = pool.run(items)
             pool.close()
             mism = sum(1 for k in range(n_sample)

@@ -21,6 +21,8 @@ strique_ctx::~strique_ctx() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (cudaEvent_t e : copy_ev) if (e) cudaEventDestroy(e);
 }
 
 extern "C" int strique_version(void) { return 100; }

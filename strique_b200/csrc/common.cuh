@@ -37,6 +37,8 @@ struct DevBuf {
 struct strique_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device upload of raw reads, overlapped with conditioning
+    cudaEvent_t copy_ev[8] = {nullptr};
     int num_sms = 0;
     std::string error;
     int64_t launches = 0;

@@ -38,17 +38,43 @@ static int stage_condition(strique_ctx *ctx, const strique_pore_constants &pore,
     TRY(d_vals.ensure(ctx, (size_t)n_reads * 256 * 4));
     TRY(d_stats.ensure(ctx, (size_t)n_reads * CS_STRIDE * 8));
     const void *raw_dev = raw;
+    const CondModel cm = to_cond_model(pore);
     stage_mark(ctx, 2 * STRIQUE_STAGE_H2D);
-    if (memspace != STRIQUE_DEVICE) {
-        TRY(d_raw.ensure(ctx, (size_t)total * esz));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_raw.p, raw, (size_t)total * esz, cudaMemcpyHostToDevice, ctx->stream));
-        raw_dev = d_raw.p;
-    }
     CUDA_TRY(ctx, cudaMemcpyAsync(d_off.p, raw_offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     stage_mark(ctx, 2 * STRIQUE_STAGE_H2D + 1);
     stage_mark(ctx, 2 * STRIQUE_STAGE_CONDITION);
-    TRY(condition_run_device(ctx, raw_kind, raw_dev, d_off.as<int64_t>(), raw_offsets, n_reads, to_cond_model(pore),
-                             want_raw, d_flt.p, d_codes.as<uint16_t>(), d_vals.as<float>(), d_stats.as<double>()));
+    if (memspace != STRIQUE_DEVICE) {
+        // Host-resident reads: upload in up to 8 slices of whole reads on a second stream; the conditioning of
+        // slice k (one CTA per read) runs while slice k + 1 crosses PCIe.
+        TRY(d_raw.ensure(ctx, (size_t)total * esz));
+        TRY(ctx->buf("cond.tmpA").ensure(ctx, total));           // sized once: the slices must not re-allocate them
+        TRY(ctx->buf("cond.tmpB").ensure(ctx, total));
+        raw_dev = d_raw.p;
+        if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        const int n_slices = (int)std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(n_reads, total * (int64_t)esz >> 22)));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));       // earlier work may still read pl.raw (and the buffers may have moved)
+        int r0 = 0;
+        for (int k = 0; k < n_slices; ++k) {
+            // slice boundaries by samples, so slices carry equal bytes
+            int r1 = r0;
+            const int64_t want = total * (k + 1) / n_slices;
+            while (r1 < n_reads && (raw_offsets[r1] < want || r1 == r0)) ++r1;
+            if (k == n_slices - 1) r1 = n_reads;
+            if (r1 == r0) continue;
+            const size_t b0 = (size_t)raw_offsets[r0] * esz, b1 = (size_t)raw_offsets[r1] * esz;
+            CUDA_TRY(ctx, cudaMemcpyAsync((char *)d_raw.p + b0, (const char *)raw + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (!ctx->copy_ev[k]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[k], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+            TRY(condition_run_device(ctx, raw_kind, raw_dev, d_off.as<int64_t>() + r0, raw_offsets + r0, r1 - r0, cm, want_raw,
+                                     d_flt.p, d_codes.as<uint16_t>(), d_vals.as<float>() + (size_t)r0 * 256,
+                                     d_stats.as<double>() + (size_t)r0 * CS_STRIDE));
+            r0 = r1;
+        }
+    } else {
+        TRY(condition_run_device(ctx, raw_kind, raw_dev, d_off.as<int64_t>(), raw_offsets, n_reads, cm, want_raw, d_flt.p,
+                                 d_codes.as<uint16_t>(), d_vals.as<float>(), d_stats.as<double>()));
+    }
     stage_mark(ctx, 2 * STRIQUE_STAGE_CONDITION + 1);
     *raw_dev_out = raw_dev;
     return STRIQUE_OK;

@@ -22,11 +22,27 @@ LOCI = {
                 'TAGCGCGCGACTCCTGAGTTCCAGAGCTTGCTACAGGCTGCGGTTGTTTCCCTCCTTGTTTTCTTCTGGTTAATCTTTATCAGGTCTTTTCTTGTTCAC'
                 'CCTCAGCGAGTACTGTGAGAGCAAGTAGTGGGGAGAGAGGGTGGGAAAAAC'),
     'fmr1': ('CGG',
-             'AGCGGGCCGGGGGTTCGGCCTCAGTCAGGCGCTCAGCTCCGTTTCGGTTTCACTTCCGGTGGAGGGCCGCCTCTGAGCGGGCGGCGGGCCGACGGCGAG'
-             'CGCGGGCGGCGGCGGTGACGGAGGCGCCGCTGCCAGGGGGCGTGCGGCAGC',
-             'GAGGCGGCGGCGGCGGCGGCGGCGGCGGCGGCTGGGCCTCGAGCGCCCGCAGCCCACCTCTCGGGGGCGGGCTCCCGGCGCTAGCAGGGCTGAAGAGAA'
-             'GATGGAGGAGCTGGTGGTGGAAGTGCGGGGCTCCAATGGCGCTTTCTACAA'),
+             'GCGGGCCGGGGGTTCGGCCTCAGTCAGGCGCTCAGCTCCGTTTCGGTTTCACTTCCGGTGGAGGGCCGCCTCTGAGCGGGCGGCGGGCCGACGGCGAGCG'
+             'CGGGCGGCGGCGGTGACGGAGGCGCCGCTGCCAGGGGGCGTGCGGCAGCG',
+             'AGGCGGCGGCGGCGGCGGCGGCGGCGGCGGCTGGGCCTCGAGCGCCCGCAGCCCACCTCTCGGGGGCGGGCTCCCGGCGCTAGCAGGGCTGAAGAGAAGA'
+             'TGGAGGAGCTGGTGGTGGAAGTGCGGGGCTCCAATGGCGCTTTCTACAAG'),
+    # Panel loci of configuration C4 (BASELINE.json configs[3]).  The reference ships no entry for them: the
+    # repeat units are the real ones (ATXN10 ATTCT, DMPK CTG), the flanks are SYNTHETIC stand-ins of mixed
+    # length (100 / 300 nt and 300 / 200 nt -> 570 ... 1770 template samples per flank alignment), drawn once
+    # with numpy default_rng(20261017); configs/panel_config.tsv carries the same strings.
+    'atxn10': ('ATTCT',
+               'TGTTGGCCAGAGTTAGTATCGATACGAAAACTGCGCGCAAATTTAAAGGATTTCGAACGTGCTCTGGCACGTCAAGCGTATGATTTTCTCTGACGTACTG',
+               'TTTCTGAATCGTTTAGTCTAAAAGTACTCCATTCTTGGCCTGTTTTCGTATTGAGAGGTCGTACGATGCAACGACCCTTAAATCGTGTTAAGATCGAAGG'
+               'TCGTTCTGTAGAATTTTATATTCTCTCCACCTAAATTTTATACCGTCTTGGAGTTTTTCGGGGGCACCGCGCCACCAGTCCGTTAGATTATCTGAGATAC'
+               'TCGTCGCAAGCCTAAGAAGCTAATCGGCGCTATTCGAAAGAAGTTCTTGCTTTTTATAAGCAACAGCGCCCATAAGCTTAATACATGTCCGACACAGCAC'),
+    'dmpk': ('CTG',
+             'CAGACTCGCACGGATGGGGGCCGTGCCCAACGCTCAGGTTTGGGAGAAGAGACCGTGGAAGGCGGGGTGGTATCCGTTTCCTGGGGTCCTGTCACAGTTC'
+             'GTCACTCAAGATCTGCGTCACGGCGAAGCAGCTCGGTTCCGAAAATGCAACTCCGGTGAGGAGCAAGCATCTCCGAATTGCGAAGGTTACCTTCCCCTCG'
+             'GGTACCAGCCCCGATCCATGTGGGGGCCATCTATTCACGCCGGCTTGGTCCCGTTATACTCGTCAGCAGACGGTAAGGGGACACCGGGAGGGGTGAACCC',
+             'GGCGAACGGCGGTTCTGCGTCGTAAAAGGGCGCGTGCCCGACCGGGCTTGGCGTCGCAGGCAGGGTTCCTCCTCTAGCGCTGGAGAAGCCGGAGGCGGTA'
+             'TTTGCTATGACAACGGGGTCAGGGCATATCCCGCAGGTGAGTATTCATCCAAAGAGCGTCGCCGCCCTTTCTCAATCCTCATACTCGGGGACTGTCTGCG'),
 }
+PANEL = ('c9orf72', 'fmr1', 'atxn10', 'dmpk')
 
 
 def encode(seq):

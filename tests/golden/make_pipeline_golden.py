@@ -27,6 +27,10 @@ SETS = [
     ('c2_small', dict(n_reads=16, seed=4242, loci=('c9orf72',), n_lo=2, n_hi=300), False),
     ('c3_mod', dict(n_reads=8, seed=4343, loci=('c9orf72',), n_lo=2, n_hi=200, mod_fraction=0.5), True),
     ('c4_panel', dict(n_reads=8, seed=4444, loci=('c9orf72', 'fmr1'), n_lo=2, n_hi=200), False),
+    # all four panel loci: flank templates of 570 / 870 / 1170 / 1770 samples, repeat units of 3, 5 and 6 nt
+    ('c4_panel4', dict(n_reads=12, seed=4545, loci=('c9orf72', 'fmr1', 'atxn10', 'dmpk'), n_lo=2, n_hi=150), False),
+    # long-expansion stress (C5): ~4000 repeats, ~200 k samples, one read per strand
+    ('c5_long', dict(n_reads=2, seed=4646, loci=('c9orf72',), fixed_n=4000, flank=4000), False),
 ]
 
 

@@ -34,7 +34,7 @@ def check(row, got):
     assert (int(got[4]), int(got[5]), got[6]) == (row['offset'], row['ticks'], row['mod'])
 
 
-@pytest.mark.parametrize('tag,idx', [('c2_small', (11, 5)), ('c3_mod', (6,)), ('c4_panel', (2,))])
+@pytest.mark.parametrize('tag,idx', [('c2_small', (11, 5)), ('c3_mod', (6,)), ('c4_panel', (2,)), ('c4_panel4', (3, 5))])
 def test_oracle_with_c_aligner_reproduces_golden(tag, idx, model_file, mod_model_file):
     from oracle import reference_path as rp
     reads, s = reads_of(tag, model_file, mod_model_file)
@@ -57,5 +57,8 @@ def test_cuda_path_reproduces_golden(tag, ctx, model_file, mod_model_file):
     got = dt.detect_batch([(name, sig, strand) for name, sig, strand, _ in reads])
     for row, g in zip(s['rows'], got):
         check(row, g)
-    # counts of noisy reads equal the simulated truth on this set
-    assert sum(g[0] == r['n_true'] for g, r in zip(got, s['rows'])) >= len(got) - 1
+    # counts of noisy reads equal the simulated truth (c5: within one unit in 4000).  ATTCT is the exception the
+    # reference itself has: for a unit shorter than k its repeatHMM profile spans 9 k-mers = 1.8 units per pass
+    # (scripts/STRique.py:329-334), so it reports ~n/1.8 -- reproduced, not corrected.
+    ok = [abs(g[0] - r['n_true']) <= (1 if tag == 'c5_long' else 0) for g, r in zip(got, s['rows']) if r['target'] != 'atxn10']
+    assert sum(ok) >= len(ok) - 1

@@ -15,6 +15,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--seed', type=int, default=1000)
+    ap.add_argument('--host', action='store_true', help='pass pinned HOST buffers (the e2e path)')
     ap.add_argument('--strand', default='', help="keep only reads of this strand ('+' or '-'): one HMM, no model hand-over")
     a = ap.parse_args()
     import torch
@@ -32,9 +33,17 @@ def main():
     raw_np, off, kind = _lib.Context._pack_raw([s for _, s, _, _ in reads])
     raw_dev = torch.from_numpy(raw_np).cuda()
     torch.cuda.synchronize()
+    import time
+    raw_pinned = torch.from_numpy(raw_np).pin_memory()
     for i in range(a.steps):
-        ctx.detect_batch(cfg, raw_dev.data_ptr(), off, kind, tids, memspace=_lib.DEVICE)
-        print(i, {k: round(v, 1) for k, v in ctx.stage_ms().items()}, flush=True)
+        t0 = time.perf_counter()
+        if a.host:
+            ctx.detect_batch(cfg, raw_pinned.numpy(), off, kind, tids, memspace=_lib.HOST)
+        else:
+            ctx.detect_batch(cfg, raw_dev.data_ptr(), off, kind, tids, memspace=_lib.DEVICE)
+        wall = (time.perf_counter() - t0) * 1e3
+        st = ctx.stage_ms()
+        print(i, 'wall %.1f ms, stages %.1f ms' % (wall, sum(st.values())), {k: round(v, 1) for k, v in st.items()}, flush=True)
 
 
 if __name__ == '__main__':
