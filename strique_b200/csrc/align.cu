@@ -3,6 +3,8 @@
 
 #include <math.h>
 
+#include <type_traits>
+
 namespace strique {
 
 namespace {
@@ -230,10 +232,15 @@ struct LinSweep {
             for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
         }
         int code_nx = codes[clampi(1 - lane, 0, N - 1)];
-        auto track_best = [&](const int j) {
-            float last = Sv[S - 1];
+        // LASTFULL: the flank ends on the last row of its lane (L == nl * R, e.g. 870 = 29 * 30), so the last DP row
+        // is the lane's bottom cell and needs no select chain
+        auto track_best = [&](const int j, auto lastfull) {
+            float last = Sv[R - 1];
+            if (!decltype(lastfull)::value) {
+                last = Sv[S - 1];
 #pragma unroll
-            for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
+                for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
+            }
             const bool upd = lane == lastlane && last > best;      // strict >: first maximum wins (dp_scout.h:175)
             best = upd ? last : best;
             bestj = upd ? j : bestj;
@@ -265,15 +272,17 @@ struct LinSweep {
 #pragma unroll
                     for (int r = 0; r < R; ++r) ckS[o + r] = Sv[r];
                 }
-                track_best(j);
+                track_best(j, std::false_type{});
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) lutc[k] = lutn[k];
             code_nx = code_nx2;
         };
         // steady step: every lane is at a column 2 <= j <= N, so the column body runs unguarded (idle
-        // lanes >= nl compute on zeros); only the checkpoint stores are conditional
-        auto steady = [&](const int st, const float (&lc)[K], float (&ln)[K]) {
+        // lanes >= nl compute on zeros).  CK: some lane may sit on a checkpoint column at this step (only the
+        // first nl steps of every ALIGN_CKPT); the other steps carry no checkpoint code at all.
+        auto steady = [&](const int st, const float (&lc)[K], float (&ln)[K], auto with_ck, auto lastfull) {
+            constexpr bool CK = decltype(with_ck)::value;
             const int j = st - lane;
             {
                 const float *row = lut_lane + (size_t)code_nx * row_len;
@@ -283,28 +292,43 @@ struct LinSweep {
             const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);
             if (lane == 0) inS = 0.f;
-            const bool ck = (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
-            const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1;
-            if (ck) {                             // H of the checkpoint column: S of the previous column + g_h
+            const bool ck = CK && (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
+            const size_t o = CK ? (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R + 1 : 0;
+            if (CK && ck) {                       // H of the checkpoint column: S of the previous column + g_h
 #pragma unroll
                 for (int r = 0; r < R; ++r) ckH[o + r] = Sv[r] + gh;
             }
             const float diag = diag_next;
             diag_next = inS;
             botS = column<false>(Sv, lc, diag, inS, gh, gv);
-            if (ck) {
+            if (CK && ck) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) ckS[o + r] = Sv[r];
             }
-            track_best(j);
+            track_best(j, lastfull);
             code_nx = code_nx2;
+        };
+        auto steady_loop = [&](int &s, auto lastfull) {
+            while (s + 1 <= N) {
+                const int m = s & (ALIGN_CKPT - 1);
+                if (m >= nl && m <= ALIGN_CKPT - 2) {
+                    // both steps of every pair stay inside [nl, ALIGN_CKPT - 1] (mod ALIGN_CKPT): no lane checkpoints
+                    int pairs = min((ALIGN_CKPT - m) >> 1, (N - s + 1) >> 1);
+                    for (; pairs > 0; --pairs, s += 2) {
+                        steady(s, lutc, lutn, std::false_type{}, lastfull);
+                        steady(s + 1, lutn, lutc, std::false_type{}, lastfull);
+                    }
+                } else {
+                    steady(s, lutc, lutn, std::true_type{}, lastfull);
+                    steady(s + 1, lutn, lutc, std::true_type{}, lastfull);
+                    s += 2;
+                }
+            }
         };
         int s = 1;
         for (; s <= nl && s <= last_step; ++s) general(s);
-        for (; s + 1 <= N; s += 2) {
-            steady(s, lutc, lutn);
-            steady(s + 1, lutn, lutc);
-        }
+        if (kL == K - 1) steady_loop(s, std::true_type{});
+        else steady_loop(s, std::false_type{});
         for (; s <= last_step; ++s) general(s);
     }
 };
