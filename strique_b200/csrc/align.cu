@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGrou
 template <int K, int S>
 int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
     const bool lin = align_params_linear(b.p);
-    int grid = ctx->num_sms * (lin ? ALIGN_WARPS_PER_SM_LINEAR : ALIGN_WARPS_PER_SM);
+    int grid = ctx->num_sms * (lin ? (getenv("STRIQUE_SCAN_WARPS") ? atoi(getenv("STRIQUE_SCAN_WARPS")) : ALIGN_WARPS_PER_SM_LINEAR) : ALIGN_WARPS_PER_SM);
     if (grid > g.n_tasks) grid = g.n_tasks;
     if (lin)
         align_scan_kernel<K, S, true><<<grid, 32, 0, ctx->stream>>>(b, g);

@@ -19,4 +19,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:alig
 echo "== ncu full: viterbi"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:viterbi_profile -c 1 -f -o "$OUT/viterbi_$TAG" \
     python bench.py --batch 2048 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_viterbi_$TAG.log" 2>&1
+echo "== ncu full: trace"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:align_trace -c 1 -f -o "$OUT/trace_$TAG" \
+    python bench.py --batch 2048 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_trace_$TAG.log" 2>&1
 ls -la "$OUT"

@@ -33,7 +33,21 @@ def main():
     raw_np, off, kind = _lib.Context._pack_raw([s for _, s, _, _ in reads])
     raw_dev = torch.from_numpy(raw_np).cuda()
     torch.cuda.synchronize()
+    import threading
     import time
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    samples = []
+    stop = threading.Event()
+
+    def sampler():
+        while not stop.is_set():
+            samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                            pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            time.sleep(0.002)
+    threading.Thread(target=sampler, daemon=True).start()
     raw_pinned = torch.from_numpy(raw_np).pin_memory()
     for i in range(a.steps):
         t0 = time.perf_counter()
@@ -43,7 +57,12 @@ def main():
             ctx.detect_batch(cfg, raw_dev.data_ptr(), off, kind, tids, memspace=_lib.DEVICE)
         wall = (time.perf_counter() - t0) * 1e3
         st = ctx.stage_ms()
-        print(i, 'wall %.1f ms, stages %.1f ms' % (wall, sum(st.values())), {k: round(v, 1) for k, v in st.items()}, flush=True)
+        t1 = time.perf_counter()
+        mine = [x for x in samples if t0 <= x[0] <= t1]
+        clk = [x[1] for x in mine]
+        print(i, 'wall %.1f ms, stages %.1f ms' % (wall, sum(st.values())), {k: round(v, 1) for k, v in st.items()},
+              'sm MHz min/med/max %d/%d/%d' % (min(clk), sorted(clk)[len(clk) // 2], max(clk)) if clk else '',
+              'W max %.0f' % max(x[2] for x in mine) if mine else '', 'reasons %s' % sorted({hex(x[3]) for x in mine}), flush=True)
 
 
 if __name__ == '__main__':
