@@ -350,16 +350,16 @@ def main():
                               'frac': vit_eups * VITERBI_LANE_OPS_PER_EDGE / fp64_peak,
                               'ops_per_edge': VITERBI_LANE_OPS_PER_EDGE, 'gcups': vit_eups / 1e9,
                               'ms_per_step': stages['viterbi_count'] / args.steps,
-                              # back-pointers: 256 B per time step written once (+ read on traceback)
-                              'hbm_GBps': t_total * args.steps * 256 / max(vit_s, 1e-9) / 1e9,
+                              # back-pointers: 128 B per time step written, 128 B read by the traceback, 8 B sample
+                              'hbm_GBps': t_total * args.steps * 264 / max(vit_s, 1e-9) / 1e9,
                               'hbm_peak_GBps': peaks.get('hbm_gbs')},
         }
         dom = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
         roofline = dict(kernels[dom])
         # DRAM traffic per launch of the dominant kernel, from the ncu --set full capture in profiles/
-        # (viterbi: 516 B per time step measured vs 512 B algorithmic; scan: 0.04 B per cell)
-        traffic = t_total * 516.0 if dom == 'viterbi_count' else (cells / args.steps) * 0.0425
-        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01m.txt scaled to this launch',
+        # (viterbi: 251 B per time step measured vs 264 B algorithmic; scan: 0.043 B per cell)
+        traffic = t_total * 251.0 if dom == 'viterbi_count' else (cells / args.steps) * 0.0428
+        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01s.txt scaled to this launch',
                          'peak_source': 'issue peak = N_SM x lanes x SM clock sampled under load (fp32: 128 lanes/SM, '
                                         'fp64: 64 lanes/SM); HBM peak: ' +
                                         ('of measured (MEASURED_PEAKS.json)' if peaks else 'of fallback 6650 GB/s')})
