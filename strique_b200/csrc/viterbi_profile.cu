@@ -57,10 +57,6 @@ struct TabGlobal {
     __device__ __forceinline__ double operator()(int k) const { return __ldg(base + k * 32); }
 };
 
-__device__ __forceinline__ double pick4(const double v[pf::P], int q) {
-    return q == 0 ? v[0] : (q == 1 ? v[1] : (q == 2 ? v[2] : v[3]));
-}
-
 constexpr unsigned FULL = 0xffffffffu;
 
 struct ModelScalars {                               // warp-uniform
@@ -98,7 +94,8 @@ __device__ __forceinline__ void init_state(pf::State &S, int lane, int p_start) 
 
 // E1 of the next column + delete chain of the column just finished, for NS sequences decoded side by side (one
 // basic block: the constants of the model are fetched once and the NS dependency chains interleave).
-template <int NS>
+// XQ = in-lane index of the position that feeds the repeat loop (compile time: no select chain per column).
+template <int NS, int XQ>
 __device__ __forceinline__ void block(const pf::Regs &R, const AuxShared &aux, const ModelScalars &ms,
                                       pf::State (&S)[NS], uint32_t (&bits)[NS]) {
     double pM3[NS], pI3[NS], pM2[NS], xm[NS], xd[NS], a[NS][pf::P], A[NS];
@@ -107,7 +104,7 @@ __device__ __forceinline__ void block(const pf::Regs &R, const AuxShared &aux, c
         pM3[i] = __shfl_up_sync(FULL, S[i].M[3], 1);
         pI3[i] = __shfl_up_sync(FULL, S[i].I[3], 1);
         pM2[i] = __shfl_up_sync(FULL, S[i].M[2], 1);
-        const double vm = pick4(S[i].M, ms.xq), vi = pick4(S[i].I, ms.xq);
+        const double vm = S[i].M[XQ], vi = S[i].I[XQ];
         xm[i] = __shfl_sync(FULL, ms.xm_slot ? vi : vm, ms.xlane);
         xd[i] = __shfl_sync(FULL, ms.xd_slot ? vi : vm, ms.xlane);
     }
@@ -131,7 +128,7 @@ __device__ __forceinline__ void block(const pf::Regs &R, const AuxShared &aux, c
 }
 
 // columns t0 .. t1 of NS sequences (t1 <= T of each); xcur[i] = sample t0 - 1 on entry, sample t1 on exit
-template <int NS>
+template <int NS, int XQ>
 __device__ __forceinline__ void forward(const pf::Regs &R, const AuxShared &aux, const ModelScalars &ms,
                                         const VitProfModelDev &m, const int lane, pf::State (&S)[NS],
                                         const SeqCtx (&c)[NS], double (&xcur)[NS], const int t0, const int t1) {
@@ -154,7 +151,7 @@ __device__ __forceinline__ void forward(const pf::Regs &R, const AuxShared &aux,
         }
 #pragma unroll
         for (int i = 0; i < NS; ++i) word[i] = pf::e2_emit(aux, S[i], eM[i], eI[i]);
-        block<NS>(R, aux, ms, S, dbits);
+        block<NS, XQ>(R, aux, ms, S, dbits);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             c[i].bp[(size_t)t * 32 + lane] = word[i] | dbits[i];
@@ -273,6 +270,61 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
     __syncwarp();
 }
 
+// the sequences of one warp in one CTA task
+template <int XQ>
+__device__ __forceinline__ void run_task(const VitProfBatch &b, const VitProfModelDev &m, const VitCtaTask &ct,
+                                         const pf::Regs &R, const AuxShared &aux, const ModelScalars &ms,
+                                         uint32_t *stage, const int lane, const int warp) {
+    // this warp's sequences: neighbours in the length order of the task (first one is the longer)
+    const int first = ct.first + warp * PROF_SEQS;
+    const int mine = min(PROF_SEQS, ct.count - warp * PROF_SEQS);
+    if (mine <= 0) return;
+    if (PROF_SEQS == 2 && mine == 2) {
+        SeqCtx c[2] = {seq_ctx(b, b.order[first]), seq_ctx(b, b.order[first + 1])};
+        if (c[1].T > c[0].T) { const SeqCtx t = c[0]; c[0] = c[1]; c[1] = t; }
+        pf::State S[2];
+        uint32_t bits[2];
+        double xcur[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            init_state(S[i], lane, ms.p_start);
+            xcur[i] = c[i].T > 0 ? __ldg(c[i].x) : 0.0;
+        }
+        block<2, XQ>(R, aux, ms, S, bits);                     // column 0: delete chain from START
+        c[0].bp[lane] = bits[0];
+        c[1].bp[lane] = bits[1];
+        forward<2, XQ>(R, aux, ms, m, lane, S, c, xcur, 1, c[1].T);
+        double best1, best0;
+        int barg1, barg0;
+        end_edges(m, S[1], stage, lane, best1, barg1);
+        {
+            pf::State S0[1] = {S[0]};
+            const SeqCtx c0[1] = {c[0]};
+            double x0[1] = {xcur[0]};
+            forward<1, XQ>(R, aux, ms, m, lane, S0, c0, x0, c[1].T + 1, c[0].T);
+            end_edges(m, S0[0], stage, lane, best0, barg0);
+        }
+        traceback(b, m, c[0], stage, lane, ms.p_start, best0, barg0);
+        traceback(b, m, c[1], stage, lane, ms.p_start, best1, barg1);
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < mine; ++k) {
+            const SeqCtx c0[1] = {seq_ctx(b, b.order[first + k])};
+            pf::State S0[1];
+            uint32_t bits[1];
+            init_state(S0[0], lane, ms.p_start);
+            double x0[1] = {c0[0].T > 0 ? __ldg(c0[0].x) : 0.0};
+            block<1, XQ>(R, aux, ms, S0, bits);
+            c0[0].bp[lane] = bits[0];
+            forward<1, XQ>(R, aux, ms, m, lane, S0, c0, x0, 1, c0[0].T);
+            double best0;
+            int barg0;
+            end_edges(m, S0[0], stage, lane, best0, barg0);
+            traceback(b, m, c0[0], stage, lane, ms.p_start, best0, barg0);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_profile_kernel(VitProfBatch b) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_task;
@@ -306,53 +358,11 @@ __global__ void __launch_bounds__(PROF_WARPS * 32, PROF_CTAS_PER_SM) viterbi_pro
         ms.lo = m.lo; ms.hi = m.hi;
         __syncthreads();
     }
-    // this warp's sequences: neighbours in the length order of the task (first one is the longer)
-    const int first = ct.first + warp * PROF_SEQS;
-    const int mine = min(PROF_SEQS, ct.count - warp * PROF_SEQS);
-    if (mine <= 0) continue;
-    if (PROF_SEQS == 2 && mine == 2) {
-        SeqCtx c[2] = {seq_ctx(b, b.order[first]), seq_ctx(b, b.order[first + 1])};
-        if (c[1].T > c[0].T) { const SeqCtx t = c[0]; c[0] = c[1]; c[1] = t; }
-        pf::State S[2];
-        uint32_t bits[2];
-        double xcur[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            init_state(S[i], lane, ms.p_start);
-            xcur[i] = c[i].T > 0 ? __ldg(c[i].x) : 0.0;
-        }
-        block<2>(R, aux, ms, S, bits);                     // column 0: delete chain from START
-        c[0].bp[lane] = bits[0];
-        c[1].bp[lane] = bits[1];
-        forward<2>(R, aux, ms, m, lane, S, c, xcur, 1, c[1].T);
-        double best1, best0;
-        int barg1, barg0;
-        end_edges(m, S[1], stage, lane, best1, barg1);
-        {
-            pf::State S0[1] = {S[0]};
-            const SeqCtx c0[1] = {c[0]};
-            double x0[1] = {xcur[0]};
-            forward<1>(R, aux, ms, m, lane, S0, c0, x0, c[1].T + 1, c[0].T);
-            end_edges(m, S0[0], stage, lane, best0, barg0);
-        }
-        traceback(b, m, c[0], stage, lane, ms.p_start, best0, barg0);
-        traceback(b, m, c[1], stage, lane, ms.p_start, best1, barg1);
-    } else {
-#pragma unroll 1
-        for (int k = 0; k < mine; ++k) {
-            const SeqCtx c0[1] = {seq_ctx(b, b.order[first + k])};
-            pf::State S0[1];
-            uint32_t bits[1];
-            init_state(S0[0], lane, ms.p_start);
-            double x0[1] = {c0[0].T > 0 ? __ldg(c0[0].x) : 0.0};
-            block<1>(R, aux, ms, S0, bits);
-            c0[0].bp[lane] = bits[0];
-            forward<1>(R, aux, ms, m, lane, S0, c0, x0, 1, c0[0].T);
-            double best0;
-            int barg0;
-            end_edges(m, S0[0], stage, lane, best0, barg0);
-            traceback(b, m, c0[0], stage, lane, ms.p_start, best0, barg0);
-        }
+    switch (ms.xq) {
+        case 0: run_task<0>(b, m, ct, R, aux, ms, stage, lane, warp); break;
+        case 1: run_task<1>(b, m, ct, R, aux, ms, stage, lane, warp); break;
+        case 2: run_task<2>(b, m, ct, R, aux, ms, stage, lane, warp); break;
+        default: run_task<3>(b, m, ct, R, aux, ms, stage, lane, warp); break;
     }
   }
 }
