@@ -158,7 +158,7 @@ typedef struct {
 
 int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc, int32_t *model_id);
 /* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, 4000 = profile kernel
- * (4 positions per lane), otherwise the team kernel shape as wps*1000 + high_slots*100 + low_slots*10 +
+ * (4 positions per lane), 32 = small-model kernel (one state per lane, values in registers), otherwise the team kernel shape as wps*1000 + high_slots*100 + low_slots*10 +
  * chain_slots (diagnostic) */
 int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id);
 /*

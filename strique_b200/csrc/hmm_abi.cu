@@ -184,7 +184,8 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     for (int s = 0; s < n_seq; ++s) {
         const HmmModel &m = *ctx->models[seq_model[s]];
         const bool profile = m.has_profile && !force_generic && !force_team;
-        const bool fast = !profile && m.shape.wps > 0 && !force_generic;
+        const bool small = !profile && !force_generic && !force_team && viterbi_small_fits(m.dev);
+        const bool fast = !profile && !small && m.shape.wps > 0 && !force_generic;
         Group *g = nullptr;
         for (Group &c : groups)
             if (c.profile == profile && c.fast == fast &&
@@ -269,7 +270,10 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                 b.bp = d_bp.as<unsigned long long>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
                 b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
                 b.queue = d_queue.as<int>();
-                TRY(viterbi_launch(ctx, *ctx->models[g.model], b));
+                if (!force_generic && !force_team && viterbi_small_fits(ctx->models[g.model]->dev))
+                    TRY(viterbi_small_launch(ctx, *ctx->models[g.model], b));
+                else
+                    TRY(viterbi_launch(ctx, *ctx->models[g.model], b));
             } else {
                 // CTA tasks: per model, runs of `teams` consecutive (length-sorted) sequences; longest task first
                 const int teams = viterbi_fast_teams(g.shape);
@@ -339,6 +343,7 @@ extern "C" int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc
 extern "C" int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id) {
     if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size()) return -1;
     if (ctx->models[model_id]->has_profile) return 4000;
+    if (viterbi_small_fits(ctx->models[model_id]->dev)) return 32;
     const VitFastShape &s = ctx->models[model_id]->shape;
     return s.wps * 1000 + s.nh * 100 + s.nl * 10 + s.qc;
 }

@@ -137,6 +137,9 @@ struct VitBatch {
 };
 
 int viterbi_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
+// small-model kernel (viterbi_small.cu): <= 32 emitting states, no chain, <= 8 in-edges per state
+bool viterbi_small_fits(const VitModelDev &m);
+int viterbi_small_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
 // team kernel: packs the model if one of the instantiated shapes fits (sets m->shape), launch
 int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
 int viterbi_fast_launch(strique_ctx *ctx, const VitFastShape &shape, const VitFastBatch &b);
