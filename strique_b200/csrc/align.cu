@@ -76,10 +76,11 @@ struct Sweep {
         const int lastlane, const int kL, float &best, int &bestj, float *__restrict__ ckS,
         float *__restrict__ ckH, const int ckpt_rows,
         // trace
-        uint32_t *__restrict__ trace, const int capture_j, float &capS, float &capH, float &capV) {
+        uint32_t *__restrict__ trace, const int capture_j, float &capS, float &capH, float &capV,
+        // floats per code in the score table (the table may have been built for more levels per lane than K)
+        const int row_len = 32 * K) {
         const float INF = STRIQUE_SEQAN_INF;
         const float geh = p.gap_extension_h, gev = p.gap_extension_v, goh = p.gap_open_h, gov = p.gap_open_v;
-        const int row_len = 32 * K;
         float lutc[K], lutn[K];
         float botS = 0.f, botV = INF;
         const int last_step = (j1 - j0) + nl - 1;
@@ -431,14 +432,118 @@ __device__ __forceinline__ int nearest_signal_index(const int32_t *rows, int L, 
     return j;
 }
 
+struct TraceCursor {
+    int tj, ti;          // cell the traceback stands on (meaningful in lane 0)
+    unsigned tv;
+    int state;
+    bool first;
+};
+enum { ST_MAIN = 0, ST_VRUN = 1, ST_HRUN = 2 };
+
+// One checkpoint block (j0, j1] of one task: recompute SeqAn's trace flags with KP levels per lane, then let lane 0
+// follow the traceback through the block.  KP <= the K the score table was built for: the traceback only moves
+// towards smaller rows, so a block entered at DP row `need` is swept with the fewest rows per lane that still
+// cover rows 1..need (cells below the cursor cannot influence the cells above it).  Returns 1 when the
+// traceback ended inside the block.
+template <int KP, int S>
+__device__ __forceinline__ int trace_block(const AlignBatch &b, const TaskGeom &g, const int lut_row_len, const int blk,
+                                           const int j1, const int bj, const int need, uint32_t *trace, int32_t *rows,
+                                           TraceCursor &c) {
+    constexpr int R = KP * S;
+    const int lane = threadIdx.x;
+    const float INF = STRIQUE_SEQAN_INF;
+    const int j0 = blk * ALIGN_CKPT;
+    const int nl = (need + R - 1) / R;
+    const int lastlane = (g.L - 1) / R, kL = ((g.L - 1) % R) / S;   // only used by the first block (need == L)
+    float Sv[R], Hv[R];
+    float diag0;
+    if (blk == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r + 1;
+            Sv[r] = i <= g.L ? g.col0[i] : 0.f;
+            Hv[r] = INF;
+        }
+        diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
+    } else {
+        const float *ckS = b.ckpt + b.ckpt_off[g.t] + (size_t)(blk - 1) * 2 * b.ckpt_rows;
+        const float *ckH = ckS + b.ckpt_rows;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r + 1;
+            Sv[r] = i <= g.L ? ckS[i] : 0.f;
+            Hv[r] = i <= g.L ? ckH[i] : INF;
+        }
+        diag0 = lane == 0 ? 0.f : (lane * R <= g.L ? ckS[lane * R] : 0.f);
+    }
+    float capS = 0.f, capH = 0.f, capV = 0.f, dummy_best = 0.f;
+    int dummy_j = 0;
+    Sweep<KP, S, true>::run(g.codes, g.N, g.lut, j0, j1, lane, nl, b.p, Sv, Hv, diag0, lastlane, kL, dummy_best, dummy_j,
+                            nullptr, nullptr, 0, trace, c.first ? bj : -1, capS, capH, capV, lut_row_len);
+    __syncwarp();
+    if (c.first) {
+        capS = __shfl_sync(0xffffffffu, capS, lastlane);
+        capH = __shfl_sync(0xffffffffu, capH, lastlane);
+        capV = __shfl_sync(0xffffffffu, capV, lastlane);
+    }
+    int done = 0;
+    if (lane == 0) {
+        int tj = c.tj, ti = c.ti, state = c.state;
+        unsigned tv = c.tv;
+        bool need_fetch = false;
+        if (c.first) {
+            tv = trace_at<KP, S>(trace, j0, tj, ti);
+            // _correctTraceValue (dp_algorithm_impl.h:1168-1185)
+            if (capV == capS) tv = (tv & ~T_DIAG) | T_MAXV;
+            else if (capH == capS) tv = (tv & ~T_DIAG) | T_MAXH;
+            // _retrieveInitialTraceDirection, PreferGapsAtEnd (dp_traceback_impl.h:456-481)
+            if (tv & T_MAXV) tv &= (T_VER | T_VOPEN | T_MAXV);
+            else if (tv & T_MAXH) tv &= (T_HOR | T_HOPEN | T_MAXH);
+        } else {
+            need_fetch = true;   // paused on a cell of this (earlier) block
+        }
+        for (;;) {
+            if (need_fetch) {
+                if (tj <= j0 && tj > 0 && ti > 0) break;   // cell lies in an earlier block
+                tv = trace_at<KP, S>(trace, j0, tj, ti);
+                need_fetch = false;
+            }
+            if (state == ST_MAIN) {
+                if (!(tj > 0 && ti > 0 && tv != 0)) { done = 1; break; }
+                if (tv & T_DIAG) {
+                    rows[ti - 1] = tj << 1; --tj; --ti; need_fetch = true;
+                } else if ((tv & T_MAXV) && (tv & T_VER)) {
+                    state = ST_VRUN;
+                } else if ((tv & T_MAXV) && (tv & T_VOPEN)) {
+                    rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
+                } else if ((tv & T_MAXH) && (tv & T_HOR)) {
+                    state = ST_HRUN;
+                } else if ((tv & T_MAXH) && (tv & T_HOPEN)) {
+                    --tj; need_fetch = true;
+                } else { done = 1; break; }
+            } else if (state == ST_VRUN) {
+                const bool cont = (!(tv & T_VOPEN) || (tv & T_VER)) && ti != 1;
+                rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
+                if (!cont) state = ST_MAIN;
+            } else {
+                const bool cont = (!(tv & T_HOPEN) || (tv & T_HOR)) && tj != 1;
+                --tj; need_fetch = true;
+                if (!cont) state = ST_MAIN;
+            }
+        }
+        c.tj = tj; c.ti = ti; c.state = state; c.tv = tv;
+    }
+    c.first = false;
+    return __shfl_sync(0xffffffffu, done, 0);
+}
+
 template <int K, int S>
 __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGroup grp) {
     constexpr int R = K * S;
     constexpr int W = (R + 7) / 8;
+    constexpr int K2 = (K + 1) / 2, K4 = (K + 3) / 4, K8 = (K + 7) / 8;   // fewer levels per lane for blocks entered at a small row
     const int lane = threadIdx.x;
-    const float INF = STRIQUE_SEQAN_INF;
     uint32_t *trace = b.trace + (size_t)blockIdx.x * ALIGN_CKPT * 32 * W;
-    enum { ST_MAIN = 0, ST_VRUN = 1, ST_HRUN = 2 };
     for (;;) {
         int q = 0;
         if (lane == 0) q = atomicAdd(b.queue + 1, 1);
@@ -451,100 +556,27 @@ __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGrou
         // traceback cursor (meaningful in lane 0).  bj < 0: no last-row score ever exceeded SeqAn's
         // "infinity" -> traceback starts at (0,0) and every flank sample is a trailing vertical gap
         // behind all N signal samples; bj == 0: best cell in DP column 0 -> all leading gaps.
-        int tj = bj < 0 ? g.N : bj, ti = g.L;
+        TraceCursor c;
+        c.tj = bj < 0 ? g.N : bj; c.ti = g.L; c.tv = 0; c.state = ST_MAIN; c.first = true;
         if (bj > 0) {
-            unsigned tv = 0;
-            int state = ST_MAIN;
-            bool first = true;
             int blk = (bj - 1) / ALIGN_CKPT;
             int j1 = bj;
             for (;;) {
-                const int j0 = blk * ALIGN_CKPT;
-                float Sv[R], Hv[R];
-                float diag0;
-                if (blk == 0) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int i = lane * R + r + 1;
-                        Sv[r] = i <= g.L ? g.col0[i] : 0.f;
-                        Hv[r] = INF;
-                    }
-                    diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
-                } else {
-                    const float *ckS = b.ckpt + b.ckpt_off[g.t] + (size_t)(blk - 1) * 2 * b.ckpt_rows;
-                    const float *ckH = ckS + b.ckpt_rows;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int i = lane * R + r + 1;
-                        Sv[r] = ckS[i];
-                        Hv[r] = ckH[i];
-                    }
-                    diag0 = lane == 0 ? 0.f : ckS[lane * R];
-                }
-                float capS = 0.f, capH = 0.f, capV = 0.f, dummy_best = 0.f;
-                int dummy_j = 0;
-                Sweep<K, S, true>::run(g.codes, g.N, g.lut, j0, j1, lane, g.nl, b.p, Sv, Hv, diag0, g.lastlane, g.kL,
-                                       dummy_best, dummy_j, nullptr, nullptr, 0, trace, first ? bj : -1, capS, capH,
-                                       capV);
+                // rows the traceback can still visit in this block (lane 0 owns the cursor)
+                const int need = max(1, __shfl_sync(0xffffffffu, c.ti, 0));
+                int done;
+                if (need <= 32 * K8 * S) done = trace_block<K8, S>(b, g, 32 * K, blk, j1, bj, need, trace, rows, c);
+                else if (need <= 32 * K4 * S) done = trace_block<K4, S>(b, g, 32 * K, blk, j1, bj, need, trace, rows, c);
+                else if (need <= 32 * K2 * S) done = trace_block<K2, S>(b, g, 32 * K, blk, j1, bj, need, trace, rows, c);
+                else done = trace_block<K, S>(b, g, 32 * K, blk, j1, bj, need, trace, rows, c);
                 ++n_blocks;
-                __syncwarp();
-                if (first) {
-                    capS = __shfl_sync(0xffffffffu, capS, g.lastlane);
-                    capH = __shfl_sync(0xffffffffu, capH, g.lastlane);
-                    capV = __shfl_sync(0xffffffffu, capV, g.lastlane);
-                }
-                int done = 0;
-                if (lane == 0) {
-                    bool need_fetch = false;
-                    if (first) {
-                        tv = trace_at<K, S>(trace, j0, tj, ti);
-                        // _correctTraceValue (dp_algorithm_impl.h:1168-1185)
-                        if (capV == capS) tv = (tv & ~T_DIAG) | T_MAXV;
-                        else if (capH == capS) tv = (tv & ~T_DIAG) | T_MAXH;
-                        // _retrieveInitialTraceDirection, PreferGapsAtEnd (dp_traceback_impl.h:456-481)
-                        if (tv & T_MAXV) tv &= (T_VER | T_VOPEN | T_MAXV);
-                        else if (tv & T_MAXH) tv &= (T_HOR | T_HOPEN | T_MAXH);
-                    } else {
-                        need_fetch = true;   // paused on a cell of this (earlier) block
-                    }
-                    for (;;) {
-                        if (need_fetch) {
-                            if (tj <= j0 && tj > 0 && ti > 0) break;   // cell lies in an earlier block
-                            tv = trace_at<K, S>(trace, j0, tj, ti);
-                            need_fetch = false;
-                        }
-                        if (state == ST_MAIN) {
-                            if (!(tj > 0 && ti > 0 && tv != 0)) { done = 1; break; }
-                            if (tv & T_DIAG) {
-                                rows[ti - 1] = tj << 1; --tj; --ti; need_fetch = true;
-                            } else if ((tv & T_MAXV) && (tv & T_VER)) {
-                                state = ST_VRUN;
-                            } else if ((tv & T_MAXV) && (tv & T_VOPEN)) {
-                                rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
-                            } else if ((tv & T_MAXH) && (tv & T_HOR)) {
-                                state = ST_HRUN;
-                            } else if ((tv & T_MAXH) && (tv & T_HOPEN)) {
-                                --tj; need_fetch = true;
-                            } else { done = 1; break; }
-                        } else if (state == ST_VRUN) {
-                            const bool cont = (!(tv & T_VOPEN) || (tv & T_VER)) && ti != 1;
-                            rows[ti - 1] = (tj << 1) | 1; --ti; need_fetch = true;
-                            if (!cont) state = ST_MAIN;
-                        } else {
-                            const bool cont = (!(tv & T_HOPEN) || (tv & T_HOR)) && tj != 1;
-                            --tj; need_fetch = true;
-                            if (!cont) state = ST_MAIN;
-                        }
-                    }
-                }
-                done = __shfl_sync(0xffffffffu, done, 0);
-                first = false;
                 if (done || blk == 0) break;
                 --blk;
-                j1 = j0;
+                j1 = blk * ALIGN_CKPT + ALIGN_CKPT;
                 __syncwarp();
             }
         }
+        const int tj = c.tj, ti = c.ti;
         if (lane == 0) {
             // leading gaps (head) or the degenerate all-gap cases: remaining flank rows are vertical gaps
             for (int i = ti; i >= 1; --i) rows[i - 1] = (tj << 1) | 1;
