@@ -22,7 +22,10 @@
 
 namespace strique {
 
-constexpr int ALIGN_CKPT = 512;          // columns between DP-column checkpoints
+#ifndef STRIQUE_ALIGN_CKPT
+#define STRIQUE_ALIGN_CKPT 512
+#endif
+constexpr int ALIGN_CKPT = STRIQUE_ALIGN_CKPT;   // columns between DP-column checkpoints (power of two)
 constexpr int ALIGN_WARPS_PER_SM = 8;    // resident single-warp CTAs per SM for the scan
 constexpr int ALIGN_WARPS_PER_SM_LINEAR = 16;   // ... for the linear-gap scan (half the registers)
 

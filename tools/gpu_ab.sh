@@ -8,7 +8,7 @@ mkdir -p "$OUT"
 for lib in variants/*.so; do
   name=$(basename "$lib" .so)
   echo "== $name"
-  STRIQUE_LIB="$PWD/$lib" timeout 600 python -m pytest tests -m gpu -x -q -k "viterbi or pipeline or golden" 2>&1 | tail -2
+  STRIQUE_LIB="$PWD/$lib" timeout 600 python -m pytest tests -m gpu -x -q -k "${STRIQUE_AB_K:-viterbi or pipeline or golden}" 2>&1 | tail -2
   STRIQUE_LIB="$PWD/$lib" timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline "$@" 2> "$OUT/bench_${TAG}_$name.err" | tee "$OUT/bench_${TAG}_$name.json" | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
