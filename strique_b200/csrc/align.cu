@@ -21,7 +21,11 @@ __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? l
 // an fp32 rounding midpoint is reported in lut_fix so the host can re-evaluate it with libm and
 // patch it -- this keeps the table bit-identical to the reference's.
 // ---------------------------------------------------------------------------------------------
-__global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S, int n_tasks) {
+// Distances beyond `far` (host: ((off - min) * (1 + 1e-5))^(1/1.2)) score exactly dist_min without evaluating pow:
+// there pow(d, 1.2) exceeds off - min by far more than any rounding in the chain, so off - fx <= min.  With the
+// reference's parameters (off 16, min 0) that is every |v - y| > 10.08, about three quarters of the table.
+__global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S, int n_tasks,
+                                       const float far) {
     const int t = blockIdx.y;
     if (t >= n_tasks) return;
     const int K = task_K[t], S = task_S[t];
@@ -40,6 +44,7 @@ __global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, cons
         if (u < nlev) {
             const float h = vals[c], v = lev[(u * S) / b.samples];
             const float d = h > v ? h - v : v - h;
+            if (d > far) { lut[e] = b.p.dist_min; continue; }
             const double x = pow((double)d, 1.2);
             const float fx = (float)x;
             const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
@@ -668,7 +673,10 @@ int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t 
     if (n_tasks == 0) return STRIQUE_OK;
     if (n_tasks > 65535) FAIL(ctx, STRIQUE_EINVAL, "alignment chunk larger than 65535 tasks");
     dim3 grid(16, n_tasks);
-    align_build_lut_kernel<<<grid, 256, 0, ctx->stream>>>(b, task_K, task_S, n_tasks);
+    float far = INFINITY;
+    const double span = (double)b.p.dist_offset - (double)b.p.dist_min;
+    if (span > 0.0 && span < 1e30) far = (float)(pow(span * (1.0 + 1e-5), 1.0 / 1.2) * (1.0 + 1e-6));
+    align_build_lut_kernel<<<grid, 256, 0, ctx->stream>>>(b, task_K, task_S, n_tasks, far);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return STRIQUE_OK;
