@@ -12,7 +12,7 @@ echo "== bench" ; timeout 900 python bench.py --steps 3 --warmup 3 2> "$OUT/benc
 tail -5 "$OUT/bench_$TAG.err"
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_$TAG.csv" \
-    python bench.py --batch 1024 --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/bench_under_ncu_$TAG.log" 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/bench_under_ncu_$TAG.log" 2>&1
 echo "== ncu full: scan"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:align_scan -c 1 -f -o "$OUT/scan_$TAG" \
     python bench.py --batch 2048 --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_scan_$TAG.log" 2>&1

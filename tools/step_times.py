@@ -16,6 +16,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--seed', type=int, default=1000)
     ap.add_argument('--host', action='store_true', help='pass pinned HOST buffers (the e2e path)')
+    ap.add_argument('--sample-ms', type=float, default=2.0, help='NVML sampling period (0: no sampler thread)')
     ap.add_argument('--strand', default='', help="keep only reads of this strand ('+' or '-'): one HMM, no model hand-over")
     a = ap.parse_args()
     import torch
@@ -46,8 +47,9 @@ def main():
             samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
                             pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
-            time.sleep(0.002)
-    threading.Thread(target=sampler, daemon=True).start()
+            time.sleep(a.sample_ms / 1e3)
+    if a.sample_ms > 0:
+        threading.Thread(target=sampler, daemon=True).start()
     raw_pinned = torch.from_numpy(raw_np).pin_memory()
     for i in range(a.steps):
         t0 = time.perf_counter()
