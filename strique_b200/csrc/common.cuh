@@ -103,6 +103,22 @@ inline int DevBuf::ensure(strique_ctx *ctx, size_t bytes) {
         if (_rc != STRIQUE_OK) return _rc;                                                        \
     } while (0)
 
+// STRIQUE_HOST_TIMING=1: report host-side sections that take longer than 3 ms (GPU-idle gaps between stages)
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+struct HostTimer {
+    const char *what;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit HostTimer(const char *w) : what(w), t0(std::chrono::steady_clock::now()), on(getenv("STRIQUE_HOST_TIMING") != nullptr) {}
+    ~HostTimer() {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 3.0) fprintf(stderr, "[host] %-28s %.1f ms\n", what, ms);
+    }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // per-stage device timing: events 2*stage (begin) and 2*stage+1 (end) on the context's stream

@@ -156,6 +156,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                              int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,
                              uint16_t *path_host) {
     if (n_seq == 0) return STRIQUE_OK;
+    HostTimer ht_all("viterbi_run_device_multi");
     const int64_t total = x_off_host[n_seq];
     const int n_models = (int)ctx->models.size();
     for (int s = 0; s < n_seq; ++s) {
@@ -199,7 +200,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     TRY(d_models.ensure(ctx, (size_t)n_models * sizeof(VitFastModelDev)));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_models.p, fast_models.data(), (size_t)n_models * sizeof(VitFastModelDev), cudaMemcpyHostToDevice, ctx->stream));
     size_t free_b = 0, total_b = 0;
-    CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    { HostTimer ht("vit cudaMemGetInfo"); CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b)); }
     const int64_t budget_bytes = (int64_t)std::max<size_t>((size_t)2 << 30, (size_t)((free_b + d_bp.cap) * 0.7));
     std::vector<int64_t> bpoff(n_seq, 0);
     for (Group &g : groups) {
@@ -262,7 +263,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                 b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
                 b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
                 TRY(viterbi_profile_launch(ctx, b, grid));
-                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors are read by the async copies
+                { HostTimer ht("vit profile kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }   // host vectors are read by the async copies
             } else if (!g.fast) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
                 VitBatch b;
@@ -318,6 +319,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
             i0 = i1;
         }
     }
+    HostTimer ht_res("vit results d2h + sync");
     CUDA_TRY(ctx, cudaMemcpyAsync(results_host, d_res.p, (size_t)n_seq * sizeof(VitResult), cudaMemcpyDeviceToHost, ctx->stream));
     if (pattern_host) CUDA_TRY(ctx, cudaMemcpyAsync(pattern_host, d_pat.p, total, cudaMemcpyDeviceToHost, ctx->stream));
     if (path_host) CUDA_TRY(ctx, cudaMemcpyAsync(path_host, d_path.p, total * 2, cudaMemcpyDeviceToHost, ctx->stream));

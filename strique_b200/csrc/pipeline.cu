@@ -208,6 +208,7 @@ extern "C" int strique_detect_batch(strique_ctx *ctx, const strique_detect_confi
                              std::vector<int64_t> &xoff_all, std::vector<int> &seq_read) -> int {
         vres.clear(); xoff_all.assign(1, 0); seq_read.clear();
         if (reads.empty()) return STRIQUE_OK;
+        HostTimer ht_stage(mod_stage ? "hmm stage (mod)" : "hmm stage (count)");
         std::vector<int> ord(reads);
         auto model_of = [&](int r) { const Target &t = *ctx->targets[read_target[r]]; return mod_stage ? t.mod_model : t.count_model; };
         std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return model_of(a) < model_of(b); });
@@ -226,6 +227,7 @@ extern "C" int strique_detect_batch(strique_ctx *ctx, const strique_detect_confi
             xoff_all.push_back(xoff_all.back() + sg.len);
         }
         const int n = (int)segs.size();
+        HostTimer ht_prep("hmm stage: after seg build");
         TRY(d_segs.ensure(ctx, (size_t)n * sizeof(PrepSeg)));
         TRY(d_x.ensure(ctx, std::max<int64_t>(1, xoff_all.back()) * 8));
         CUDA_TRY(ctx, cudaMemcpyAsync(d_segs.p, segs.data(), (size_t)n * sizeof(PrepSeg), cudaMemcpyHostToDevice, ctx->stream));
