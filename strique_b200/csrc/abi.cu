@@ -13,9 +13,12 @@ std::string g_strique_create_error;
 strique_ctx::~strique_ctx() {
     for (auto &kv : bufs)
         if (kv.second.p) cudaFree(kv.second.p);
-    for (void *p : owned) cudaFree(p);
-    for (auto *m : models) delete m;
-    for (auto *t : targets) delete t;
+    if (helper) { delete helper; helper = nullptr; }
+    if (!is_helper) {
+        for (void *p : owned) cudaFree(p);
+        for (auto *m : models) delete m;
+        for (auto *t : targets) delete t;
+    }
     for (auto &e : stage_ev)
         if (e) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);

@@ -53,6 +53,10 @@ struct strique_ctx {
     std::vector<strique::HmmModel *> models;
     std::vector<strique::Target *> targets;
     std::map<std::string, DevBuf> bufs;   // persistent device scratch
+    // second batch in flight (pipeline.cu): a helper context with its own stream and scratch that shares this
+    // context's models and targets; is_helper contexts do not own them
+    strique_ctx *helper = nullptr;
+    bool is_helper = false;
     DevBuf &buf(const char *name) { return bufs[name]; }
     ~strique_ctx();
 };
