@@ -38,6 +38,11 @@ struct Smem {
     unsigned chist[256];
     double bc[8];
     int ibc[8];
+    // ranks that share a key prefix share one histogram (pass 0: all of them; later passes: usually the two
+    // neighbours of a median / percentile)
+    unsigned long long gpre[MAXR];
+    int grp[MAXR];
+    int ngrp;
 };
 
 __device__ __forceinline__ double block_sum(double v, Smem &sm) {
@@ -64,40 +69,53 @@ __device__ void multi_select(const T *__restrict__ data, const int n, const int 
     typedef typename KT::Key Key;
     const int tid = threadIdx.x;
     if (tid < MAXR) { sm.prefix[tid] = 0; sm.krem[tid] = tid < nr ? sm.ranks[tid] : 0; }
+    __syncthreads();
     for (int pass = 0; pass < KT::BYTES; ++pass) {
         const int shift = (KT::BYTES - 1 - pass) * 8;
         for (int i = tid; i < MAXR * 256; i += CT) (&sm.hist[0][0])[i] = 0;
+        if (tid == 0) {
+            int ng = 0;
+            for (int r = 0; r < nr; ++r) {
+                int g = 0;
+                while (g < ng && sm.gpre[g] != sm.prefix[r]) ++g;
+                if (g == ng) sm.gpre[ng++] = sm.prefix[r];
+                sm.grp[r] = g;
+            }
+            sm.ngrp = ng;
+        }
         __syncthreads();
+        const int ng = sm.ngrp;
         Key pre[MAXR];
         unsigned lastbin[MAXR], cnt[MAXR];
 #pragma unroll
-        for (int r = 0; r < MAXR; ++r) { pre[r] = (Key)sm.prefix[r]; lastbin[r] = 0; cnt[r] = 0; }
+        for (int g = 0; g < MAXR; ++g) { pre[g] = (Key)sm.gpre[g < ng ? g : 0]; lastbin[g] = 0; cnt[g] = 0; }
         for (int i = tid; i < n; i += CT) {
             const Key k = KT::to_key(data[i]);
             const unsigned bin = (unsigned)(k >> shift) & 255u;
             const Key hi = pass == 0 ? (Key)0 : (Key)(k >> (shift + 8 < (int)sizeof(Key) * 8 ? shift + 8 : 0));
 #pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                if (r < nr && hi == pre[r]) {
-                    if (cnt[r] && lastbin[r] == bin) {
-                        ++cnt[r];
+            for (int g = 0; g < MAXR; ++g) {
+                if (g < ng && hi == pre[g]) {
+                    if (cnt[g] && lastbin[g] == bin) {
+                        ++cnt[g];
                     } else {
-                        if (cnt[r]) atomicAdd(&sm.hist[r][lastbin[r]], cnt[r]);
-                        lastbin[r] = bin;
-                        cnt[r] = 1;
+                        if (cnt[g]) atomicAdd(&sm.hist[g][lastbin[g]], cnt[g]);
+                        lastbin[g] = bin;
+                        cnt[g] = 1;
                     }
                 }
             }
         }
 #pragma unroll
-        for (int r = 0; r < MAXR; ++r)
-            if (cnt[r]) atomicAdd(&sm.hist[r][lastbin[r]], cnt[r]);
+        for (int g = 0; g < MAXR; ++g)
+            if (cnt[g]) atomicAdd(&sm.hist[g][lastbin[g]], cnt[g]);
         __syncthreads();
         if (tid < nr) {
+            const unsigned *h = sm.hist[sm.grp[tid]];
             int k = sm.krem[tid];
             unsigned d = 0;
             for (; d < 255; ++d) {
-                const int c = (int)sm.hist[tid][d];
+                const int c = (int)h[d];
                 if (k < c) break;
                 k -= c;
             }
