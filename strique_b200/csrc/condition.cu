@@ -151,16 +151,48 @@ __device__ __forceinline__ int reflect(int k, int n) {   // scipy.ndimage mode='
 template <bool IS_MAX>
 __device__ void window_pass(const uint8_t *__restrict__ in, uint8_t *__restrict__ out8, uint16_t *__restrict__ out16,
                             int n, int lo, int hi, unsigned *chist) {
-    for (int i = threadIdx.x; i < n; i += CT) {
-        int v = IS_MAX ? 0 : 255;
-        if (i + lo >= 0 && i + hi < n) {
+    // flat 8-wide window [i + lo, i + hi]; a thread produces 4 consecutive outputs from 11 inputs (the 5 inputs all
+    // four windows share are reduced once)
+    auto op = [](int a, int b) { return IS_MAX ? max(a, b) : min(a, b); };
+    for (int i = threadIdx.x * 4; i < n; i += CT * 4) {
+        int v[4];
+        if (i + lo >= 0 && i + 3 + hi < n) {
+            int x[11];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const int x = in[i + lo + k]; v = IS_MAX ? max(v, x) : min(v, x); }
+            for (int k = 0; k < 11; ++k) x[k] = in[i + lo + k];
+            const int c = op(op(op(x[3], x[4]), op(x[5], x[6])), x[7]);
+            v[0] = op(op(x[0], x[1]), op(x[2], c));
+            v[1] = op(op(x[1], x[2]), op(c, x[8]));
+            v[2] = op(op(x[2], c), op(x[8], x[9]));
+            v[3] = op(op(c, x[8]), op(x[9], x[10]));
         } else {
-            for (int k = lo; k <= hi; ++k) { const int x = in[reflect(i + k, n)]; v = IS_MAX ? max(v, x) : min(v, x); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int w = IS_MAX ? 0 : 255;
+                if (i + j < n)
+                    for (int k = lo; k <= hi; ++k) w = op(w, (int)in[reflect(i + j + k, n)]);
+                v[j] = w;
+            }
         }
-        if (out8) out8[i] = (uint8_t)v;
-        if (out16) { out16[i] = (uint16_t)v; atomicAdd(&chist[v], 1u); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < n) {
+                if (out8) out8[i + j] = (uint8_t)v[j];
+                if (out16) out16[i + j] = (uint16_t)v[j];
+            }
+        }
+        if (out16) {                    // code histogram: neighbours are mostly equal after the morphology
+            int run = 0, val = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (i + j >= n) break;
+                if (v[j] == val) { ++run; continue; }
+                if (run) atomicAdd(&chist[val], (unsigned)run);
+                val = v[j];
+                run = 1;
+            }
+            if (run) atomicAdd(&chist[val], (unsigned)run);
+        }
     }
     __syncthreads();
 }
