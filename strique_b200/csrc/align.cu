@@ -24,8 +24,13 @@ __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? l
 // Distances beyond `far` (host: ((off - min) * (1 + 1e-5))^(1/1.2)) score exactly dist_min without evaluating pow:
 // there pow(d, 1.2) exceeds off - min by far more than any rounding in the chain, so off - fx <= min.  With the
 // reference's parameters (off 16, min 0) that is every |v - y| > 10.08, about three quarters of the table.
-__global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S, int n_tasks,
-                                       const float far) {
+__global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S,
+                                                              int n_tasks, const float far) {
+    // One CTA = 32 codes of one task; a warp takes one flank level at a time with one code per lane.  The code
+    // values rise with the code, so the lanes near a level form a contiguous run and most warps see only far
+    // pairs and skip pow altogether.  The tile goes through shared memory so that the table rows (code-major)
+    // are still written coalesced.
+    extern __shared__ float tile[];                  // [32][row_len + 1]
     const int t = blockIdx.y;
     if (t >= n_tasks) return;
     const int K = task_K[t], S = task_S[t];
@@ -33,31 +38,44 @@ __global__ void align_build_lut_kernel(AlignBatch b, const int32_t *task_K, cons
     const int nlev_in = b.flank_off[f + 1] - b.flank_off[f];
     const int rows = nlev_in * b.samples;
     const int nlev = rows / S;            // levels as seen by the kernel
-    const int row_len = 32 * K;
+    const int row_len = 32 * K, pitch = row_len + 1;
     const float *vals = b.code_values + (size_t)sg * b.n_code_values;
     const float *lev = b.flank_levels + b.flank_off[f];
     float *lut = b.lut + (size_t)t * b.lut_task_stride;
-    const int total = b.n_code_values * row_len;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int c = e / row_len, u = e - c * row_len;
-        float out = 0.f;
-        if (u < nlev) {
-            const float h = vals[c], v = lev[(u * S) / b.samples];
-            const float d = h > v ? h - v : v - h;
-            if (d > far) { lut[e] = b.p.dist_min; continue; }
-            const double x = pow((double)d, 1.2);
-            const float fx = (float)x;
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
-            const long long low = (long long)(bits & 0x1FFFFFFFull) - 0x10000000ll;
-            if ((low < 0 ? -low : low) <= 16 && b.lut_fix != nullptr) {
-                unsigned long long k = atomicAdd(b.lut_fix, 1ull);
-                if (k < (unsigned long long)b.lut_fix_cap)
-                    b.lut_fix[1 + k] = ((unsigned long long)t << 40) | (unsigned long long)e;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int c0 = blockIdx.x * 32; c0 < b.n_code_values; c0 += gridDim.x * 32) {
+        const int c = c0 + lane;
+        const float h = c < b.n_code_values ? vals[c] : 0.f;
+        for (int u = warp; u < row_len; u += n_warps) {
+            float out = 0.f;
+            if (u < nlev && c < b.n_code_values) {
+                const float v = lev[(u * S) / b.samples];
+                const float d = h > v ? h - v : v - h;
+                if (d > far) {
+                    out = b.p.dist_min;
+                } else {
+                    const double x = pow((double)d, 1.2);
+                    const float fx = (float)x;
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+                    const long long low = (long long)(bits & 0x1FFFFFFFull) - 0x10000000ll;
+                    if ((low < 0 ? -low : low) <= 16 && b.lut_fix != nullptr) {
+                        unsigned long long k = atomicAdd(b.lut_fix, 1ull);
+                        if (k < (unsigned long long)b.lut_fix_cap)
+                            b.lut_fix[1 + k] = ((unsigned long long)t << 40) | (unsigned long long)(c * row_len + u);
+                    }
+                    const float s = b.p.dist_offset - fx;
+                    out = s > b.p.dist_min ? s : b.p.dist_min;
+                }
             }
-            const float s = b.p.dist_offset - fx;
-            out = s > b.p.dist_min ? s : b.p.dist_min;
+            tile[lane * pitch + u] = out;
         }
-        lut[e] = out;
+        __syncthreads();
+        const int n_codes = min(32, b.n_code_values - c0);
+        for (int e = threadIdx.x; e < n_codes * row_len; e += blockDim.x) {
+            const int cc = e / row_len, u = e - cc * row_len;
+            lut[(size_t)(c0 + cc) * row_len + u] = tile[cc * pitch + u];
+        }
+        __syncthreads();
     }
 }
 
@@ -672,11 +690,14 @@ int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t 
                            int n_tasks) {
     if (n_tasks == 0) return STRIQUE_OK;
     if (n_tasks > 65535) FAIL(ctx, STRIQUE_EINVAL, "alignment chunk larger than 65535 tasks");
-    dim3 grid(16, n_tasks);
+    dim3 grid(8, n_tasks);
     float far = INFINITY;
     const double span = (double)b.p.dist_offset - (double)b.p.dist_min;
     if (span > 0.0 && span < 1e30) far = (float)(pow(span * (1.0 + 1e-5), 1.0 / 1.2) * (1.0 + 1e-6));
-    align_build_lut_kernel<<<grid, 256, 0, ctx->stream>>>(b, task_K, task_S, n_tasks, far);
+    const size_t smem = (size_t)32 * (b.lut_row + 1) * sizeof(float);     // lut_row = 32 * Kmax of the batch
+    if (smem > 48 * 1024)
+        CUDA_TRY(ctx, cudaFuncSetAttribute(align_build_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    align_build_lut_kernel<<<grid, 256, smem, ctx->stream>>>(b, task_K, task_S, n_tasks, far);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return STRIQUE_OK;
