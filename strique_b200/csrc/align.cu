@@ -170,7 +170,9 @@ struct Sweep {
                 botS = cS;
                 botV = cV;
                 if (TRACE) {
-                    uint32_t *dst = trace + ((size_t)(j - j0 - 1) * 32 + lane) * W;
+                    // [lane][column][W]: the traceback mostly moves along a diagonal, i.e. through consecutive columns of
+                    // one lane's strip -- 8 of them share a 128-byte line of the walker's L1
+                    uint32_t *dst = trace + ((size_t)lane * ALIGN_CKPT + (j - j0 - 1)) * W;
 #pragma unroll
                     for (int w = 0; w < W; ++w) dst[w] = tw[w];
                 } else {
@@ -433,7 +435,7 @@ __device__ __forceinline__ unsigned trace_at(const uint32_t *trace, int j0, int 
     constexpr int W = (R + 7) / 8;
     if (i <= 0 || j <= 0) return 0u;   // DP row 0 carries no trace; column 0 is never followed
     const int li = (i - 1) / R, r = (i - 1) % R;
-    const uint32_t w = __ldcg(trace + ((size_t)(j - j0 - 1) * 32 + li) * W + r / 8);
+    const uint32_t w = trace[((size_t)li * ALIGN_CKPT + (j - j0 - 1)) * W + r / 8];   // L1-cached (see the writer)
     const unsigned nib = (w >> (4 * (r % 8))) & 15u;
     const unsigned src = nib & 3u;
     return (src == 0 ? T_DIAG : (src == 1 ? T_MAXV : T_MAXH)) | ((nib & 4u) ? T_HOPEN : T_HOR) |
