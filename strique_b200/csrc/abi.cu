@@ -161,7 +161,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::max<size_t>((size_t)1 << 30, (size_t)(free_b * 0.6));
-    const int trace_warps = ctx->num_sms * (getenv("STRIQUE_TRACE_WARPS") ? atoi(getenv("STRIQUE_TRACE_WARPS")) : 8);
+    const int trace_warps = ctx->num_sms * (getenv("STRIQUE_TRACE_WARPS") ? atoi(getenv("STRIQUE_TRACE_WARPS")) : 12);   // single-warp CTAs per SM (168 registers for K = 5)
     const int fix_cap = 1 << 16;
 
     TRY(d_col0.ensure(ctx, col0.size() * sizeof(float)));
@@ -248,7 +248,9 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
                 volatile float fx = (float)pow((double)d, 1.2);
                 volatile float s = params.dist_offset - fx;
                 const float out = s > params.dist_min ? s : params.dist_min;
-                CUDA_TRY(ctx, cudaMemcpy(b.lut + (size_t)t * lut_task_stride + e, &out, 4, cudaMemcpyHostToDevice));
+                const int Kt = tK[t0 + t];                                   // stored [u % K][u / K] inside the code row
+                const int64_t pos = (int64_t)c * row_len + (u % Kt) * 32 + u / Kt;
+                CUDA_TRY(ctx, cudaMemcpy(b.lut + (size_t)t * lut_task_stride + pos, &out, 4, cudaMemcpyHostToDevice));
             }
         }
         // ---- groups by kernel instantiation, longest signal first -----------------------------

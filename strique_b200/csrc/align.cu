@@ -71,9 +71,12 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
         }
         __syncthreads();
         const int n_codes = min(32, b.n_code_values - c0);
+        // storage order inside a code row: [k][lane] for level u = lane * K + k, so that the scan's K loads per
+        // column are one 128-byte line each
         for (int e = threadIdx.x; e < n_codes * row_len; e += blockDim.x) {
-            const int cc = e / row_len, u = e - cc * row_len;
-            lut[(size_t)(c0 + cc) * row_len + u] = tile[cc * pitch + u];
+            const int cc = e / row_len, p = e - cc * row_len;
+            const int u = (p & 31) * K + (p >> 5);
+            lut[(size_t)(c0 + cc) * row_len + p] = tile[cc * pitch + u];
         }
         __syncthreads();
     }
@@ -108,19 +111,26 @@ struct Sweep {
         float botS = 0.f, botV = INF;
         const int last_step = (j1 - j0) + nl - 1;
         // software pipeline: scores of the next column are fetched while this one is computed
+        // position of level u = lane * K + k inside a code row of a table built for Kt levels per lane: [u % Kt][u / Kt]
+        int loff[K];
+        {
+            const int Kt = row_len >> 5;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { const int u = lane * K + k; loff[k] = (u % Kt) * 32 + u / Kt; }
+        }
         {
             const int c = codes[clampi(j0 + 1 - lane - 1, 0, N - 1)];
-            const float *row = lut + (size_t)c * row_len + lane * K;
+            const float *row = lut + (size_t)c * row_len;
 #pragma unroll
-            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
+            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + loff[k]);
         }
         int code_nx = codes[clampi(j0 + 2 - lane - 1, 0, N - 1)];
         for (int s = 1; s <= last_step; ++s) {
             const int j = j0 + s - lane;
             {
-                const float *row = lut + (size_t)code_nx * row_len + lane * K;
+                const float *row = lut + (size_t)code_nx * row_len;
 #pragma unroll
-                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k);
+                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + loff[k]);
             }
             const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];   // code of column j + 2
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);
@@ -250,12 +260,12 @@ struct LinSweep {
         float lutc[K], lutn[K];
         float botS = 0.f;
         const int last_step = N + nl - 1;
-        const float *lut_lane = lut + lane * K;
+        const float *lut_lane = lut + lane;      // code row stored [k][lane]
         {
             const int c = codes[clampi(-lane, 0, N - 1)];
             const float *row = lut_lane + (size_t)c * row_len;
 #pragma unroll
-            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k);
+            for (int k = 0; k < K; ++k) lutc[k] = __ldg(row + k * 32);
         }
         int code_nx = codes[clampi(1 - lane, 0, N - 1)];
         // LASTFULL: the flank ends on the last row of its lane (L == nl * R, e.g. 870 = 29 * 30), so the last DP row
@@ -278,7 +288,7 @@ struct LinSweep {
             {
                 const float *row = lut_lane + (size_t)code_nx * row_len;
 #pragma unroll
-                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k);
+                for (int k = 0; k < K; ++k) lutn[k] = __ldg(row + k * 32);
             }
             const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);
@@ -313,7 +323,7 @@ struct LinSweep {
             {
                 const float *row = lut_lane + (size_t)code_nx * row_len;
 #pragma unroll
-                for (int k = 0; k < K; ++k) ln[k] = __ldg(row + k);
+                for (int k = 0; k < K; ++k) ln[k] = __ldg(row + k * 32);
             }
             const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);

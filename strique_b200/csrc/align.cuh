@@ -48,7 +48,7 @@ struct AlignBatch {
     int col0_stride;
     int samples;                  // flank samples per level as given by the caller
     const int32_t *task_sig, *task_flank, *task_pre, *task_post;   // [n_tasks]
-    float *lut;                   // [n_tasks][n_code_values][lut_row]
+    float *lut;                   // [n_tasks][n_code_values][lut_row]; inside a row level u = lane * K + k sits at [k][lane]
     int64_t lut_task_stride;      // floats
     int lut_row;                  // floats per code row (32 * Kmax of the batch)
     float *ckpt;                  // checkpoints, see ckpt_off
