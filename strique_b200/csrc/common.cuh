@@ -57,6 +57,9 @@ struct strique_ctx {
     // context's models and targets; is_helper contexts do not own them
     strique_ctx *helper = nullptr;
     bool is_helper = false;
+    // cudaMemGetInfo is a driver round trip that was measured at 16 ... 65 ms per call on some (virtualised) GPU
+    // boxes: the free-memory figure behind the chunking budgets is cached and refreshed only after an allocation
+    size_t free_cached = 0, total_cached = 0;
     DevBuf &buf(const char *name) { return bufs[name]; }
     ~strique_ctx();
 };
@@ -80,6 +83,7 @@ extern std::string g_strique_create_error;
 
 inline int DevBuf::ensure(strique_ctx *ctx, size_t bytes) {
     if (bytes <= cap && p) return STRIQUE_OK;
+    ctx->free_cached = 0;   // the cached free-memory figure is stale after this
     if (bytes == 0) bytes = 16;
     if (p) cudaFree(p);
     p = nullptr;
@@ -99,6 +103,18 @@ inline int DevBuf::ensure(strique_ctx *ctx, size_t bytes) {
     }
     cap = want;
     return STRIQUE_OK;
+}
+
+// free / total device memory for the chunking budgets (cached, see strique_ctx::free_cached)
+static inline cudaError_t ctx_mem_info(strique_ctx *ctx, size_t *free_b, size_t *total_b) {
+    if (ctx->free_cached == 0) {
+        const cudaError_t e = cudaMemGetInfo(&ctx->free_cached, &ctx->total_cached);
+        if (e != cudaSuccess) { ctx->free_cached = 0; return e; }
+        if (ctx->free_cached == 0) ctx->free_cached = 1;
+    }
+    *free_b = ctx->free_cached;
+    *total_b = ctx->total_cached;
+    return cudaSuccess;
 }
 
 #define TRY(expr)                                                                                 \

@@ -200,7 +200,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     TRY(d_models.ensure(ctx, (size_t)n_models * sizeof(VitFastModelDev)));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_models.p, fast_models.data(), (size_t)n_models * sizeof(VitFastModelDev), cudaMemcpyHostToDevice, ctx->stream));
     size_t free_b = 0, total_b = 0;
-    { HostTimer ht("vit cudaMemGetInfo"); CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b)); }
+    { HostTimer ht("vit cudaMemGetInfo"); CUDA_TRY(ctx, ctx_mem_info(ctx, &free_b, &total_b)); }
     const int64_t budget_bytes = (int64_t)std::max<size_t>((size_t)2 << 30, (size_t)((free_b + d_bp.cap) * 0.7));
     std::vector<int64_t> bpoff(n_seq, 0);
     for (Group &g : groups) {
