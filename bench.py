@@ -359,7 +359,7 @@ def main():
         # DRAM traffic per launch of the dominant kernel, from the ncu --set full capture in profiles/
         # (viterbi: 251 B per time step measured vs 264 B algorithmic; scan: 0.043 B per cell)
         traffic = t_total * 251.0 if dom == 'viterbi_count' else (cells / args.steps) * 0.0428
-        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01u.txt scaled to this launch',
+        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01v.txt scaled to this launch',
                          'peak_source': 'issue peak = N_SM x lanes x SM clock sampled under load (fp32: 128 lanes/SM, '
                                         'fp64: 64 lanes/SM); HBM peak: ' +
                                         ('of measured (MEASURED_PEAKS.json)' if peaks else 'of fallback 6650 GB/s')})
