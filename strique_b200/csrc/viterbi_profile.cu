@@ -373,13 +373,17 @@ size_t viterbi_profile_smem_bytes() { return (size_t)PROF_AUX_BYTES + (size_t)PR
 
 // Largest useful grid: every resident CTA slot of the device (persistent CTAs pulling from the queues).
 int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta) {
-    const size_t smem = viterbi_profile_smem_bytes();
-    if (cudaFuncSetAttribute(viterbi_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_kernel, PROF_WARPS * 32, smem) != cudaSuccess) return 0;
-    if (per_sm < 1) per_sm = 1;
+    static int cached[64] = {0};                      // per device: the shared-memory attribute is per device too
+    int &per_sm_cached = cached[ctx->device & 63];
     if (warps_per_cta) *warps_per_cta = PROF_WARPS * PROF_SEQS;   // sequences per CTA task
-    return ctx->num_sms * per_sm;
+    if (per_sm_cached == 0) {
+        const size_t smem = viterbi_profile_smem_bytes();
+        if (cudaFuncSetAttribute(viterbi_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_kernel, PROF_WARPS * 32, smem) != cudaSuccess) return 0;
+        per_sm_cached = per_sm < 1 ? 1 : per_sm;
+    }
+    return ctx->num_sms * per_sm_cached;
 }
 
 // grid persistent CTAs pulling CTA tasks from the queue
