@@ -337,7 +337,7 @@ extern "C" int strique_align_batch(strique_ctx *ctx, const strique_align_params 
     const int total_lev = flank_offsets[n_flanks];
     DevBuf &d_in8 = ctx->buf("ab.in8"), &d_codes = ctx->buf("ab.codes"), &d_sigoff = ctx->buf("ab.sigoff"),
            &d_vals = ctx->buf("ab.vals"), &d_lev = ctx->buf("ab.lev"), &d_flankoff = ctx->buf("ab.flankoff");
-    TRY(d_codes.ensure(ctx, std::max<int64_t>(1, total) * 2));
+    TRY(d_codes.ensure(ctx, std::max<int64_t>(1, total) * 2 + 16));   // + 16: the scan prefetches up to 2 codes past a signal
     TRY(d_sigoff.ensure(ctx, (size_t)(n_signals + 1) * 8));
     TRY(d_flankoff.ensure(ctx, (size_t)(n_flanks + 1) * 4));
     const cudaMemcpyKind kind = memspace == STRIQUE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

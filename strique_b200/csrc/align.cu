@@ -317,6 +317,7 @@ struct LinSweep {
         // steady step: every lane is at a column 2 <= j <= N, so the column body runs unguarded (idle
         // lanes >= nl compute on zeros).  CK: some lane may sit on a checkpoint column at this step (only the
         // first nl steps of every ALIGN_CKPT); the other steps carry no checkpoint code at all.
+        const uint16_t *cptr = codes;           // steady loop: &codes[j + 1] of this lane, advanced every step
         auto steady = [&](const int st, const float (&lc)[K], float (&ln)[K], auto with_ck, auto lastfull) {
             constexpr bool CK = decltype(with_ck)::value;
             const int j = st - lane;
@@ -325,7 +326,9 @@ struct LinSweep {
 #pragma unroll
                 for (int k = 0; k < K; ++k) ln[k] = __ldg(row + k * 32);
             }
-            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
+            // every lane is at 1 <= j <= N here, so j + 1 needs no clamp: it reads at most 2 codes past the signal,
+            // inside the (padded) code buffer, and those values are never used
+            const int code_nx2 = *cptr++;
             float inS = __shfl_up_sync(0xffffffffu, botS, 1);
             if (lane == 0) inS = 0.f;
             const bool ck = CK && (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
@@ -345,6 +348,7 @@ struct LinSweep {
             code_nx = code_nx2;
         };
         auto steady_loop = [&](int &s, auto lastfull) {
+            cptr = codes + max(s - lane + 1, 0);     // lanes >= nl are idle (never negative for the others)
             while (s + 1 <= N) {
                 const int m = s & (ALIGN_CKPT - 1);
                 if (m >= nl && m <= ALIGN_CKPT - 2) {

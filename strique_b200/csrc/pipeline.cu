@@ -37,7 +37,7 @@ static int stage_condition(strique_ctx *ctx, const strique_pore_constants &pore,
            &d_codes = ctx->buf("pl.codes"), &d_vals = ctx->buf("pl.vals"), &d_stats = ctx->buf("pl.stats");
     TRY(d_off.ensure(ctx, (size_t)(n_reads + 1) * 8));
     TRY(d_flt.ensure(ctx, (size_t)total * esz));
-    TRY(d_codes.ensure(ctx, (size_t)total * 2));
+    TRY(d_codes.ensure(ctx, (size_t)total * 2 + 16));       // + 16: the scan prefetches up to 2 codes past a read
     TRY(d_vals.ensure(ctx, (size_t)n_reads * 256 * 4));
     TRY(d_stats.ensure(ctx, (size_t)n_reads * CS_STRIDE * 8));
     const void *raw_dev = raw;
