@@ -114,7 +114,13 @@ def test_profile_team_and_generic_kernels_agree(ctx, model_file, mod_model_file,
     g, lo, hi = hmm.repeat_mod_graph('GGCCCC', pm, pm_m)
     mid = ctx.hmm_create(hmm.compile_graph(g))
     assert ctx.hmm_kernel_shape(mid) == 32          # the methylation HMM: small-model kernel (one state per lane)
-    cases.append((mid, [np.clip(synth.simulate(pm_o, 'GGCCCC' * n + 'GGCCC', rng, noise=True), lo, hi) for n in (1, 9, 200)], False))
+    mod_segs = [np.clip(synth.simulate(pm_o, 'GGCCCC' * n + 'GGCCC', rng, noise=True), lo, hi) for n in (1, 9, 200)]
+    m_nan = mod_segs[1].copy()
+    m_nan[7] = np.nan                                    # NaN sample: log 1 in every state
+    m_out = mod_segs[1].copy()
+    m_out[11] = 1000.0                                   # outside the uniform ranges of s0 / e0 / inserts
+    mod_segs += [mod_segs[1][:1], mod_segs[1][:9], mod_segs[2][:257], m_nan, m_out, np.full(40, 1000.0), np.zeros(0)]
+    cases.append((mid, mod_segs, False))
 
     def run(env):
         for k in ('STRIQUE_VITERBI_GENERIC', 'STRIQUE_VITERBI_TEAM'):
