@@ -242,6 +242,8 @@ def main():
         raise SystemExit('bench.py: no CUDA device -- the hot path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout; the contract is ONE JSON line there
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ctx = _lib.Context(local_rank)
     dt = repeatCounter(MODEL, mod_model_file=MOD_MODEL if args.mod else None, context=ctx)
