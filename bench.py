@@ -242,9 +242,24 @@ def main():
         raise SystemExit('bench.py: no CUDA device -- the hot path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout; the contract is ONE JSON line there
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # NCCL (NCCL_DEBUG=VERSION on the GPU boxes) prints its version banner on stdout when the communicator
+        # is created; the contract is ONE JSON line there, so stdout points at stderr until that has happened
+        import ctypes
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            try:
+                ctypes.CDLL(None).fflush(None)
+            except Exception:  # noqa: BLE001
+                pass
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     ctx = _lib.Context(local_rank)
     dt = repeatCounter(MODEL, mod_model_file=MOD_MODEL if args.mod else None, context=ctx)
     for name in args.loci:
