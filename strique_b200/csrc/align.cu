@@ -277,7 +277,9 @@ struct LinSweep {
 #pragma unroll
                 for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[(k + 1) * S - 1] : last;
             }
-            const bool upd = lane == lastlane && last > best;      // strict >: first maximum wins (dp_scout.h:175)
+            // strict >: first maximum wins (dp_scout.h:175).  Every lane tracks its own bottom row; only the last
+            // lane's (best, bestj) is read after the scan, so the lane test is not needed here
+            const bool upd = last > best;
             best = upd ? last : best;
             bestj = upd ? j : bestj;
         };
