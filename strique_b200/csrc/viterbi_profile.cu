@@ -32,7 +32,10 @@ namespace strique {
 
 namespace {
 
-constexpr int PROF_WARPS = 4;                       // warps per CTA
+#ifndef PROF_WARPS_PER_CTA
+#define PROF_WARPS_PER_CTA 4
+#endif
+constexpr int PROF_WARPS = PROF_WARPS_PER_CTA;       // warps per CTA
 #ifndef PROF_SEQS
 #define PROF_SEQS 1                                 // sequences decoded side by side by one warp (1 or 2; 2 measured no faster)
 #endif
