@@ -152,7 +152,8 @@ typedef struct {
     int32_t t_first;      /* first / last sample decoded by a REPEAT state (-1: none)              */
     int32_t t_last;
     int32_t pattern_len;  /* number of repeat passes found between SEP states                      */
-    int32_t status;       /* 0 ok, 1 impossible sequence (log p = -inf), 2 internal error          */
+    int32_t status;       /* 0 ok, 1 impossible sequence (log p = -inf), 2 internal error
+                           * (3 is internal: declined by the fixed-point kernel, never returned)   */
     int32_t reserved;
 } strique_viterbi_result;
 
@@ -172,6 +173,16 @@ int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_seq, const d
 
 /* work of the last viterbi / detect call: (time steps) x (in-edges of the model), summed */
 int64_t strique_last_viterbi_edges(const strique_ctx *ctx);
+/*
+ * Linear profile models (every count model of the reference) are decoded by a fixed-point kernel: tagged int32
+ * scores at 2^-16 nat, log p = float64 re-score of the decoded path (csrc/profile_q.h).  Sequences it cannot
+ * vouch for are decoded by the float64 kernel (pomegranate's arithmetic, scripts/STRique.py:433-441) in the same
+ * call.  strique_set_viterbi_exact(ctx, 1) sends everything to the float64 kernel.  The two counters report the
+ * last viterbi / detect call: sequences decoded in fixed point, and sequences handed on to float64.
+ */
+int strique_set_viterbi_exact(strique_ctx *ctx, int exact);
+int64_t strique_last_viterbi_fixed(const strique_ctx *ctx);
+int64_t strique_last_viterbi_declined(const strique_ctx *ctx);
 
 /* ---- conditioning ---------------------------------------------------------------------------- */
 typedef struct {

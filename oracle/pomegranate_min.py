@@ -70,6 +70,9 @@ def _liboracle():
         _lib.strique_oracle_viterbi.restype = ctypes.c_int64
         _lib.strique_oracle_viterbi.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        _lib.strique_oracle_viterbi_margin.restype = ctypes.c_int64
+        _lib.strique_oracle_viterbi_margin.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     return _lib
 
 
@@ -200,8 +203,12 @@ class HiddenMarkovModel:
         cap = (T + 2) * (len(self.states) - self.silent_start + 2)
         path = np.empty(cap, dtype=np.int32)
         logp = ctypes.c_double(0.0)
-        n = _liboracle().strique_oracle_viterbi(ctypes.byref(h), x.ctypes.data, T, ctypes.byref(logp),
-                                                path.ctypes.data, cap)
+        margin = ctypes.c_double(float('inf'))
+        n = _liboracle().strique_oracle_viterbi_margin(ctypes.byref(h), x.ctypes.data, T, ctypes.byref(logp),
+                                                       path.ctypes.data, cap, ctypes.byref(margin))
+        # gap between the best and the second-best path (test infrastructure: lists the near-tie reads on which a
+        # decoder with coarser arithmetic may legitimately differ)
+        self.last_margin = margin.value
         if n < 0:
             raise MemoryError('oracle viterbi failed ({})'.format(n))
         if n == 0:

@@ -484,8 +484,10 @@ class RefRepeatCounter:
         score_prefix, prefix_begin, prefix_end = self.detect_range(morph, tc['prefix_ext'], pre_trim=trim_prefix)
         score_suffix, suffix_begin, suffix_end = self.detect_range(morph, tc['suffix_ext'], post_trim=trim_suffix)
         n, p, states, mod_pattern = 0, 0, [], '-'
+        margin = None
         if prefix_begin < suffix_end and score_prefix > 0.0 and score_suffix > 0.0:
             n, p, states = tc['repeatHMM'].count_repeats(fltn[prefix_begin:suffix_end])
+            margin = getattr(tc['repeatHMM'].model, 'last_margin', None)
             if self.pm is not self.pm_mod:
                 nrm = self.pm.normalize_minmax(raw_signal.astype(np.float64))
                 mask = np.array(['repeat' in s for s in states], dtype=bool)
@@ -493,5 +495,6 @@ class RefRepeatCounter:
                 mod_pattern = tc['modHMM'].mod_repeats(rep)
         if details is not None:
             details.update(prefix_begin=int(prefix_begin), prefix_end=int(prefix_end),
-                           suffix_begin=int(suffix_begin), suffix_end=int(suffix_end), states=states)
+                           suffix_begin=int(suffix_begin), suffix_end=int(suffix_end), states=states,
+                           margin=margin)
         return n, score_prefix, score_suffix, p, prefix_end, max(suffix_begin - prefix_end, 0), mod_pattern

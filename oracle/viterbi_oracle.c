@@ -45,8 +45,14 @@ static inline double emission(int kind, double a, double b, double c0, double c1
  * Returns the path length (>0), 0 if the sequence is impossible (log p = -inf), -1 on alloc failure,
  * -2 if path_cap is too small.
  */
-int64_t strique_oracle_viterbi(const oracle_hmm *h, const double *x, int64_t T, double *logp_out,
-                               int32_t *path_out, int64_t path_cap) {
+/*
+ * margin_out (optional): the gap between the best and the second-best complete path = the smallest
+ * difference, over the decisions ON the best path, between the winning in-edge and the best other
+ * in-edge of that state (any second-best path leaves the best one for the last time at such a decision).
+ * Reads with a gap below the arithmetic resolution of a faster decoder are its legitimate exceptions.
+ */
+int64_t strique_oracle_viterbi_margin(const oracle_hmm *h, const double *x, int64_t T, double *logp_out,
+                                      int32_t *path_out, int64_t path_cap, double *margin_out) {
     const int m = h->n_states, p = h->silent_start;
     double *v = (double *)malloc(sizeof(double) * (size_t)(T + 1) * (size_t)m);
     int32_t *tbx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(T + 1) * (size_t)m);
@@ -107,19 +113,47 @@ int64_t strique_oracle_viterbi(const oracle_hmm *h, const double *x, int64_t T, 
     {
         /* walk back, then reverse in place */
         int64_t px = T; int32_t py = h->end_index;
+        double margin = INFINITY;
         while (!(px == 0 && py == h->start_index)) {
             if (n >= path_cap) { n = -2; goto done; }
             path_out[n++] = py;
             size_t at = (size_t)px * m + (size_t)py;
             int32_t nx = tbx[at], ny = tby[at];
             if (nx < 0) { n = 0; *logp_out = -INFINITY; goto done; }
+            if (margin_out) {
+                /* best candidate of (px, py) that does not come from (nx, ny) */
+                double second = -INFINITY;
+                for (int k = h->in_ptr[py]; k < h->in_ptr[py + 1]; ++k) {
+                    int ki = h->in_src[k];
+                    double s;
+                    if (py < p) {
+                        if (px < 1) continue;
+                        double e = emission(h->dist_kind[py], h->dist_a[py], h->dist_b[py], c0[py], c1[py], x[px - 1]);
+                        if (ki == ny) continue;
+                        s = v[(size_t)(px - 1) * m + ki] + h->in_logp[k] + e;
+                    } else {
+                        if (ki == ny) continue;
+                        if (ki >= p && ki >= py) continue;           /* silent sources must precede */
+                        if (ki < p && px == 0) continue;             /* column 0 has no emitting values */
+                        s = v[(size_t)px * m + ki] + h->in_logp[k];
+                    }
+                    if (s > second) second = s;
+                }
+                if (v[at] - second < margin) margin = v[at] - second;
+            }
             px = nx; py = ny;
         }
         if (n >= path_cap) { n = -2; goto done; }
         path_out[n++] = h->start_index;
+        if (margin_out) *margin_out = margin;
         for (int64_t a = 0, b = n - 1; a < b; ++a, --b) { int32_t t = path_out[a]; path_out[a] = path_out[b]; path_out[b] = t; }
     }
 done:
     free(v); free(tbx); free(tby); free(c0); free(c1);
     return n;
+}
+
+int64_t strique_oracle_viterbi(const oracle_hmm *h, const double *x, int64_t T, double *logp_out,
+                               int32_t *path_out, int64_t path_cap) {
+    return strique_oracle_viterbi_margin(h, x, T, logp_out, path_out, path_cap, 0);
 }

@@ -121,6 +121,12 @@ def load():
                                         c_int, c_void_p, c_void_p, c_int64]
     lib.strique_last_viterbi_edges.restype = c_int64
     lib.strique_last_viterbi_edges.argtypes = [c_void_p]
+    lib.strique_last_viterbi_fixed.restype = c_int64
+    lib.strique_last_viterbi_fixed.argtypes = [c_void_p]
+    lib.strique_last_viterbi_declined.restype = c_int64
+    lib.strique_last_viterbi_declined.argtypes = [c_void_p]
+    lib.strique_set_viterbi_exact.restype = c_int
+    lib.strique_set_viterbi_exact.argtypes = [c_void_p, c_int]
     lib.strique_last_stage_ms.restype = ctypes.c_float
     lib.strique_last_stage_ms.argtypes = [c_void_p, c_int]
     lib.strique_hmm_create.restype = c_int
@@ -316,6 +322,16 @@ class Context:
     @property
     def last_viterbi_edges(self):
         return int(self.lib.strique_last_viterbi_edges(self.handle))
+
+    def set_viterbi_exact(self, exact):
+        """True: profile models are decoded by the float64 kernel only (pomegranate's arithmetic); False (default):
+        by the fixed-point kernel, with float64 for the sequences it declines."""
+        self.check(self.lib.strique_set_viterbi_exact(self.handle, 1 if exact else 0), 'strique_set_viterbi_exact')
+
+    @property
+    def last_viterbi_fixed(self):
+        """(sequences decoded in fixed point, sequences handed on to the float64 kernel) of the last call"""
+        return (int(self.lib.strique_last_viterbi_fixed(self.handle)), int(self.lib.strique_last_viterbi_declined(self.handle)))
 
 
 _default_ctx = {}

@@ -46,6 +46,10 @@ struct strique_ctx {
     int64_t last_align_cells = 0;
     float last_scan_ms = 0.f;
     int64_t last_viterbi_edges = 0;
+    // profile models: sequences decoded by the fixed-point kernel / declined by it and decoded in float64 (last call)
+    int64_t last_viterbi_fixed = 0, last_viterbi_declined = 0;
+    bool viterbi_exact = false;           // float64 kernel only (strique_set_viterbi_exact)
+    std::vector<strique_viterbi_result> vit_res_scratch;
     float stage_ms[8] = {0};              // last detect call: see STRIQUE_STAGE_* in the public header
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t stage_ev[16] = {nullptr};

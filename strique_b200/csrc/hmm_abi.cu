@@ -179,6 +179,8 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     // STRIQUE_VITERBI_GENERIC / STRIQUE_VITERBI_TEAM force the generic / the team kernel (A/B parity tests)
     const bool force_generic = getenv("STRIQUE_VITERBI_GENERIC") != nullptr;
     const bool force_team = getenv("STRIQUE_VITERBI_TEAM") != nullptr;
+    // STRIQUE_VITERBI_EXACT: float64 kernel only (the fixed-point kernel is the default for models inside its bounds)
+    const bool exact_only = getenv("STRIQUE_VITERBI_EXACT") != nullptr || ctx->viterbi_exact;
     // ---- groups: all profile-kernel models, one per team-kernel shape, one per model for the generic kernel
     struct Group { bool fast; VitFastShape shape; int model; bool profile; std::vector<int32_t> ids; };
     std::vector<Group> groups;
@@ -228,42 +230,73 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                 // in its length order (they finish together, so the CTA barrier between tasks costs nothing); one
                 // queue over the tasks of all models (loci / strands), longest first: every hand-out is a whole CTA
                 // and no warp ever waits for a sequence of another warp's model.
+                // Pass 1: the fixed-point kernel for every model that has a fixed-point image; pass 2: the float64
+                // kernel for the other models and for the sequences pass 1 declined (status 3).
                 DevBuf &d_pmodels = ctx->buf("vit.prof_models");
                 std::vector<VitProfModelDev> pm(n_models);
                 for (int i = 0; i < n_models; ++i)
                     if (ctx->models[i]->has_profile) pm[i] = ctx->models[i]->profile; else memset(&pm[i], 0, sizeof(pm[i]));
-                std::vector<std::vector<int32_t>> per_model(n_models);
-                for (size_t i = i0; i < i1; ++i) per_model[seq_model[g.ids[i]]].push_back(g.ids[i]);   // keeps the length order
-                int warps_per_cta = 1;
-                int grid = viterbi_profile_max_grid(ctx, &warps_per_cta);
-                if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi_profile_kernel: occupancy query failed");
-                struct HostTask { int model; size_t first; int count; int64_t maxlen; };
-                std::vector<HostTask> tasks;
-                for (int mi = 0; mi < n_models; ++mi)
-                    for (size_t k = 0; k < per_model[mi].size(); k += warps_per_cta)
-                        tasks.push_back(HostTask{mi, k, (int)std::min<size_t>(warps_per_cta, per_model[mi].size() - k),
-                                                 len(per_model[mi][k])});
-                std::stable_sort(tasks.begin(), tasks.end(), [](const HostTask &a, const HostTask &b) { return a.maxlen > b.maxlen; });
+                TRY(d_pmodels.ensure(ctx, (size_t)n_models * sizeof(VitProfModelDev)));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_pmodels.p, pm.data(), pm.size() * sizeof(VitProfModelDev), cudaMemcpyHostToDevice, ctx->stream));
                 std::vector<int32_t> order;
                 std::vector<VitCtaTask> ctas;
-                for (const HostTask &t : tasks) {
-                    ctas.push_back(VitCtaTask{t.model, (int32_t)order.size(), t.count});
-                    order.insert(order.end(), per_model[t.model].begin() + t.first, per_model[t.model].begin() + t.first + t.count);
+                auto run_pass = [&](const std::vector<int32_t> &ids, bool fixed_point) -> int {   // ids in length order
+                    if (ids.empty()) return STRIQUE_OK;
+                    std::vector<std::vector<int32_t>> per_model(n_models);
+                    for (int32_t s : ids) per_model[seq_model[s]].push_back(s);
+                    int warps_per_cta = 1;
+                    int grid = fixed_point ? viterbi_profile_q_max_grid(ctx, &warps_per_cta) : viterbi_profile_max_grid(ctx, &warps_per_cta);
+                    if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi profile kernel: occupancy query failed");
+                    struct HostTask { int model; size_t first; int count; int64_t maxlen; };
+                    std::vector<HostTask> tasks;
+                    for (int mi = 0; mi < n_models; ++mi)
+                        for (size_t k = 0; k < per_model[mi].size(); k += warps_per_cta)
+                            tasks.push_back(HostTask{mi, k, (int)std::min<size_t>(warps_per_cta, per_model[mi].size() - k),
+                                                     len(per_model[mi][k])});
+                    std::stable_sort(tasks.begin(), tasks.end(), [](const HostTask &a, const HostTask &b) { return a.maxlen > b.maxlen; });
+                    order.clear();
+                    ctas.clear();
+                    for (const HostTask &t : tasks) {
+                        ctas.push_back(VitCtaTask{t.model, (int32_t)order.size(), t.count});
+                        order.insert(order.end(), per_model[t.model].begin() + t.first, per_model[t.model].begin() + t.first + t.count);
+                    }
+                    grid = std::min<int>(grid, (int)ctas.size());
+                    TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
+                    CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
+                    CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
+                    CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                    VitProfBatch b;
+                    b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
+                    b.n_models = n_models; b.models = d_pmodels.as<VitProfModelDev>();
+                    b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size(); b.counters = d_queue.as<int>();
+                    b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
+                    b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
+                    if (fixed_point) TRY(viterbi_profile_q_launch(ctx, b, grid)); else TRY(viterbi_profile_launch(ctx, b, grid));
+                    return STRIQUE_OK;
+                };
+                std::vector<int32_t> fixed_ids, exact_ids;
+                for (size_t i = i0; i < i1; ++i) {
+                    const int32_t s = g.ids[i];
+                    (ctx->models[seq_model[s]]->profile.qgrp && !exact_only ? fixed_ids : exact_ids).push_back(s);
                 }
-                grid = std::min<int>(grid, (int)ctas.size());
-                TRY(d_pmodels.ensure(ctx, (size_t)n_models * sizeof(VitProfModelDev)));
-                TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_pmodels.p, pm.data(), pm.size() * sizeof(VitProfModelDev), cudaMemcpyHostToDevice, ctx->stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                VitProfBatch b;
-                b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
-                b.n_models = n_models; b.models = d_pmodels.as<VitProfModelDev>();
-                b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size(); b.counters = d_queue.as<int>();
-                b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
-                b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
-                TRY(viterbi_profile_launch(ctx, b, grid));
-                { HostTimer ht("vit profile kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }   // host vectors are read by the async copies
+                if (!fixed_ids.empty()) {
+                    TRY(run_pass(fixed_ids, true));
+                    // the declined ones: read the status words back (40 bytes per sequence)
+                    std::vector<VitResult> &tmp = ctx->vit_res_scratch;
+                    tmp.resize(n_seq);
+                    CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), d_res.p, (size_t)n_seq * sizeof(VitResult), cudaMemcpyDeviceToHost, ctx->stream));
+                    { HostTimer ht("vit fixed-point kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }
+                    size_t declined = 0;
+                    for (int32_t s : fixed_ids)
+                        if (tmp[s].status == 3) { exact_ids.push_back(s); ++declined; }
+                    ctx->last_viterbi_fixed += (int64_t)(fixed_ids.size() - declined);
+                    ctx->last_viterbi_declined += (int64_t)declined;
+                    if (declined) std::stable_sort(exact_ids.begin(), exact_ids.end(), [&](int a, int b) { return len(a) > len(b); });
+                }
+                if (!exact_ids.empty()) {
+                    TRY(run_pass(exact_ids, false));
+                    { HostTimer ht("vit profile kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }   // host vectors are read by the async copies
+                }
             } else if (!g.fast) {
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
                 VitBatch b;
@@ -366,6 +399,7 @@ extern "C" int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_s
         xd = d_x.as<double>();
     }
     ctx->last_viterbi_edges = 0;
+    ctx->last_viterbi_fixed = ctx->last_viterbi_declined = 0;
     std::vector<int32_t> seq_model(n_seq, model_id);
     return viterbi_run_device_multi(ctx, seq_model.data(), xd, x_offsets, n_seq, results, pattern_out, path_out);
 }

@@ -88,6 +88,14 @@ static int stage_condition(strique_ctx *ctx, const strique_pore_constants &pore,
 using namespace strique;
 
 extern "C" int64_t strique_last_viterbi_edges(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_edges : 0; }
+extern "C" int64_t strique_last_viterbi_fixed(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_fixed : 0; }
+extern "C" int64_t strique_last_viterbi_declined(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_declined : 0; }
+extern "C" int strique_set_viterbi_exact(strique_ctx *ctx, int exact) {
+    if (!ctx) return STRIQUE_EINVAL;
+    ctx->viterbi_exact = exact != 0;
+    if (ctx->helper) ctx->helper->viterbi_exact = exact != 0;
+    return STRIQUE_OK;
+}
 extern "C" float strique_last_stage_ms(const strique_ctx *ctx, int stage) {
     return (ctx && stage >= 0 && stage < STRIQUE_N_STAGES) ? ctx->stage_ms[stage] : 0.f;
 }
@@ -222,6 +230,7 @@ static int detect_batch_serial(strique_ctx *ctx, const strique_detect_config *cf
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     stage_reset(ctx);
     ctx->last_viterbi_edges = 0;
+    ctx->last_viterbi_fixed = ctx->last_viterbi_declined = 0;
     const bool use_mod = cfg->use_mod != 0;
     // ---- 1. conditioning ------------------------------------------------------------------------
     const void *raw_dev = nullptr;

@@ -1,0 +1,254 @@
+// Lane arithmetic of the FIXED-POINT profile Viterbi kernel (viterbi_profile_q.cu), written once for device and host.
+//
+// Same model layout and recurrences as profile_core.h (positions x {M, I, D} slots, lane l owns positions
+// 4l..4l+3; replaces pomegranate 0.10.0 `HiddenMarkovModel.viterbi` for the linear profile topologies of the
+// reference, scripts/STRique.py:201-441), but the forward pass runs on TAGGED 32-bit FIXED-POINT scores:
+//
+//   * a score is an int32 in units of 2^-19 nat relative to a running column maximum; its low 3 bits are zero
+//     ("clean"), so the resolution of a value is 2^-16 nat (fp32 at |log p| ~ 1e4 resolves 1e-3);
+//   * every in-edge weight carries the NAME of its edge in its low 3 bits ("tag", larger = earlier in the
+//     reference's candidate order).  One `max(v + w, best)` -- a single VIADDMNMX on sm_100a -- therefore relaxes
+//     the edge AND keeps the winner's name: the arg-max costs no instruction, and the first candidate wins exact
+//     ties like the strict '>' of the float64 decoder;
+//   * integer sums do not round: a path's fixed-point score differs from its float64 score only by the rounding
+//     of the weights (once per model) and of the emissions (2^-17 each), never by the order of operations;
+//   * every R_NORM columns the column maximum is subtracted (renormalisation) and values more than |Q_KILL| nat
+//     below it are declared unreachable (Q_NEG).  The constants below make int32 overflow impossible.
+//
+// log p is NOT taken from the fixed-point pass: the traceback re-scores the decoded path in float64 with the
+// model's original weights and emissions, so log p is the exact score of the returned path.  The forward value and
+// the re-scored value must agree within the quantisation bound, otherwise (and for samples outside the fast
+// emission range, unreachable ends, models outside the bounds) the sequence is handed to the float64 kernel.
+//
+// Back-pointer byte of position q of a lane (4 per 32-bit word, one word per lane per column):
+//     bits 0-2  M: 7 self, 6 M_{p-1}, 5 I_{p-1}, 4 I_p, 3 M_{p-2}, 2 X_M, 1 D_{p-1}
+//     bits 3-4  I: 3 self, 2 M_p, 1 D_p
+//     bits 5-6  D: 3 M_{p-1}, 2 I_{p-1}, 1 X_D, 0 hop from D_{p-1}
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "profile_core.h"
+
+namespace strique {
+namespace pq {
+
+constexpr int P = pf::P;
+constexpr int FRAC = 16;                         // value resolution 2^-16 nat
+constexpr int TAG_BITS = 3;
+constexpr int32_t TAG_MASK = 7;
+constexpr int32_t Q_ONE = 1 << (FRAC + TAG_BITS);   // one nat
+constexpr int R_NORM = 4;                        // columns between renormalisations
+// bounds in nat (see the overflow argument in DESIGN.md 4.3): finite weights >= -W_MAX, emissions clamped to
+// >= -E_MAX, emission constants <= C0_MAX, so a value drops by at most S = W_MAX + E_MAX per column.
+constexpr int W_MAX = 12, E_MAX = 100, C0_MAX = 2, S_STEP = W_MAX + E_MAX;
+constexpr int Q_KILL_NAT = -640;                 // below this (relative to the column maximum): unreachable
+constexpr int Q_ABSENT_NAT = -1152;              // weight of an edge the model does not have
+constexpr int Q_NEG_NAT = -1152;                 // value of an unreachable state after a renormalisation
+static_assert(-Q_ABSENT_NAT >= -Q_KILL_NAT + R_NORM * S_STEP + W_MAX + R_NORM * C0_MAX, "an absent edge must lose against every live candidate");
+static_assert(Q_KILL_NAT - Q_NEG_NAT > R_NORM * S_STEP, "an unreachable state must not drift back above the kill line");
+static_assert(-Q_NEG_NAT + R_NORM * S_STEP + 2 * -Q_ABSENT_NAT + W_MAX < 4096, "int32 range (4096 nat at 2^-19)");
+constexpr int32_t Q_KILL = Q_KILL_NAT * Q_ONE, Q_ABSENT = Q_ABSENT_NAT * Q_ONE, Q_NEG = Q_NEG_NAT * Q_ONE;
+constexpr int32_t E_MIN16 = -E_MAX * (1 << FRAC);   // emission clamp in units of 2^-16
+
+// Per-lane table of a quantised model: int32 groups of four (fetched as one 16-byte word) ...
+enum : int {
+    G_WM = 0,                 // [q] {self, M_{p-1}, I_{p-1}, I_p} -> M_p                  (kept in registers)
+    G_WB = G_WM + P,          // [q] {M_{p-2} -> M_p, D_{p-1} -> M_p, I_p self, M_p -> I_p}
+    G_WC = G_WB + P,          // [q] {D_p -> I_p, M_{p-1} -> D_p, I_{p-1} -> D_p, hop D_{p-1} -> D_p}
+    G_X = G_WC + P,           // {X_M, X_D, scan round 4, 0}
+    G_CWR = G_X + 1,          // {scan rounds 0..3}: summed hop weights seen by the cross-lane scan
+    G_EI = G_CWR + 1,         // [q] I-slot emission (Uniform), already shifted: multiple of 8
+    G_TOTAL = G_EI + 1
+};
+// ... and float64 emission constants of the M slots, pairs: {mu, 1/(2 sigma^2)}[q], then {c0[0], c0[1]}, {c0[2], c0[3]}
+enum : int { E_MU = 0, E_C0 = P, E_TOTAL = P + P / 2 };
+
+struct I4 {
+    int32_t x, y, z, w;
+};
+
+PF_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+
+struct RegsQ {
+    int32_t wM[P][4];
+};
+
+struct StateQ {
+    int32_t M[P], I[P], D[P];       // last finished column (clean)
+    int32_t partM[P], partI[P];     // tagged E1 maxima of the upcoming column
+    int32_t Dprev;                  // D of the last position of the previous lane (same column as D[], clean)
+};
+
+// magic-number rounding of a float64 emission to units of 2^-16 (round to nearest even, exact for |e| < 32768)
+PF_HD int32_t to_q16(double e) {
+    const double t = e + 103079215104.0;         // 1.5 * 2^36: ulp 2^-16 in [2^36, 2^37)
+#ifdef __CUDA_ARCH__
+    return __double2loint(t);
+#else
+    union { double d; uint64_t u; } c;
+    c.d = t;
+    return (int32_t)(uint32_t)c.u;
+#endif
+}
+
+// Emissions of the M slots for sample x (inside every Uniform range, not NaN): units of 2^-16, clamped.
+template <class Tab>
+PF_HD void emissions_q(const Tab &tab, double x, int32_t eM[P]) {
+    const pf::Pair c01 = tab.dpair(E_C0), c23 = tab.dpair(E_C0 + 1);
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const pf::Pair em = tab.dpair(E_MU + q);
+        const double dx = x - em.a;
+        const double c0 = q == 0 ? c01.a : (q == 1 ? c01.b : (q == 2 ? c23.a : c23.b));
+        eM[q] = imax(to_q16(c0 - (dx * dx) * em.b), E_MIN16);
+    }
+}
+
+// E2 + emission: finishes column t from the tagged E1 maxima and the delete states of column t-1.
+// Returns the M / I back-pointer bits of the column.
+template <class Tab>
+PF_HD uint32_t e2_emit(const Tab &tab, StateQ &s, const int32_t eM[P]) {
+    const I4 ei = tab.grp(G_EI);
+    int32_t bm[P], bi[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const I4 wb = tab.grp(G_WB + q), wc = tab.grp(G_WC + q);
+        const int32_t dsrc = q == 0 ? s.Dprev : s.D[q > 0 ? q - 1 : 0];
+        bm[q] = imax(dsrc + wb.y, s.partM[q]);
+        bi[q] = imax(s.D[q] + wc.x, s.partI[q]);
+        s.M[q] = (bm[q] + eM[q] * 8) & ~TAG_MASK;
+        const int32_t eiq = q == 0 ? ei.x : (q == 1 ? ei.y : (q == 2 ? ei.z : ei.w));
+        s.I[q] = (bi[q] + eiq) & ~TAG_MASK;
+    }
+    uint32_t word = 0u;
+#pragma unroll
+    for (int q = 0; q < P; ++q) word |= ((uint32_t)(bm[q] & 7) | ((uint32_t)(bi[q] & 3) << 3)) << (8 * q);
+    return word;
+}
+
+// E1 of the next column from the emitting values of the column just finished (all clean).
+// pM3 / pI3 / pM2: M, I of the last and M of the last-but-one position of the previous lane; xm: X_M source.
+template <class Tab>
+PF_HD void e1(const RegsQ &r, const Tab &tab, StateQ &s, int32_t pM3, int32_t pI3, int32_t pM2, int32_t xm) {
+    const I4 wx = tab.grp(G_X);
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const I4 wb = tab.grp(G_WB + q);
+        const int32_t m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
+        const int32_t i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
+        const int32_t m2 = q == 0 ? pM2 : (q == 1 ? pM3 : s.M[q > 1 ? q - 2 : 0]);
+        int32_t c = s.M[q] + r.wM[q][0];
+        c = imax(m1 + r.wM[q][1], c);
+        c = imax(i1 + r.wM[q][2], c);
+        c = imax(s.I[q] + r.wM[q][3], c);
+        c = imax(m2 + wb.x, c);
+        if (q == 0) c = imax(xm + wx.x, c);
+        s.partM[q] = c;
+        s.partI[q] = imax(s.M[q] + wb.w, s.I[q] + wb.z);
+    }
+}
+
+// Delete chain, part 1: tagged entry maxima a[q] of this lane's D states and the lane composite A
+// (D of the lane's last position when nothing enters from the previous lane; its low bits are not a tag).
+template <class Tab>
+PF_HD void d_entry(const Tab &tab, const StateQ &s, int32_t pM3, int32_t pI3, int32_t xd, int32_t a[P], int32_t &A) {
+    const I4 wx = tab.grp(G_X);
+    int32_t h[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const I4 wc = tab.grp(G_WC + q);
+        const int32_t m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
+        const int32_t i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
+        int32_t c = imax(i1 + wc.z, m1 + wc.y);
+        if (q == 0) c = imax(xd + wx.y, c);
+        a[q] = c;
+        h[q] = wc.w;
+    }
+    A = a[0];
+#pragma unroll
+    for (int q = 1; q < P; ++q) A = imax(A + h[q], a[q]);
+}
+
+// One round of the cross-lane max-plus scan: Al = A of lane - 2^r.
+template <class Tab>
+PF_HD int32_t d_round(const Tab &tab, int32_t A, int32_t Al, int r) {
+    const I4 w = r < 4 ? tab.grp(G_CWR) : tab.grp(G_X);
+    const int32_t wr = r == 0 ? w.x : (r == 1 ? w.y : (r == 2 ? w.z : (r == 3 ? w.w : w.z)));
+    return imax(Al + wr, A);
+}
+
+// Delete chain, part 2: Din = scanned composite of the previous lane (its last D of this column).
+// Returns the D back-pointer bits of the column.
+template <class Tab>
+PF_HD uint32_t d_final(const Tab &tab, StateQ &s, const int32_t a[P], int32_t Din) {
+    uint32_t bits = 0u;
+    int32_t D = Din & ~TAG_MASK;
+    s.Dprev = D;
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const I4 wc = tab.grp(G_WC + q);
+        const int32_t c = imax(D + wc.w, a[q]);
+        bits |= (uint32_t)(c & 3) << (8 * q + 5);
+        D = c & ~TAG_MASK;
+        s.D[q] = D;
+    }
+    return bits;
+}
+
+// Renormalisation: largest emitting value of the lane ...
+PF_HD int32_t lane_max(const StateQ &s) {
+    int32_t m = imax(s.M[0], s.I[0]);
+#pragma unroll
+    for (int q = 1; q < P; ++q) m = imax(imax(s.M[q], s.I[q]), m);
+    return m;
+}
+// ... and the shift by the column maximum mx; values that fall below the kill line become unreachable.
+PF_HD void renorm(StateQ &s, int32_t mx) {
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int32_t m = s.M[q] - mx, i = s.I[q] - mx;
+        s.M[q] = m < Q_KILL ? Q_NEG : m;
+        s.I[q] = i < Q_KILL ? Q_NEG : i;
+    }
+}
+
+// Traceback of one step. slot: 0 M, 1 I, 2 D.  Emitting states step back one column.  `wk` receives the index
+// (pf::K_* table of the float64 model, lane = position / 4 of the TARGET state) of the weight of the edge taken.
+// Returns false on a pointer that cannot occur.
+PF_HD bool back(uint32_t word, const pf::TraceCfg &c, int &p, int &slot, int &t, int &wk) {
+    const int q = p & 3;
+    const uint32_t f = word >> (8 * q);
+    if (slot == 0) {
+        --t;
+        switch (f & 7u) {
+            case 7: wk = pf::K_WMR + q * 4; break;
+            case 6: wk = pf::K_WMR + q * 4 + 1; p -= 1; break;
+            case 5: wk = pf::K_WMR + q * 4 + 2; p -= 1; slot = 1; break;
+            case 4: wk = pf::K_WMR + q * 4 + 3; slot = 1; break;
+            case 3: wk = pf::K_WM2 + q; p -= 2; break;
+            case 2: wk = pf::K_WX; p = c.xm_src_p; slot = c.xm_src_slot; break;
+            case 1: wk = pf::K_E2 + q * 2; p -= 1; slot = 2; break;
+            default: return false;
+        }
+    } else if (slot == 1) {
+        --t;
+        switch ((f >> 3) & 3u) {
+            case 3: wk = pf::K_WI + q * 2; break;
+            case 2: wk = pf::K_WI + q * 2 + 1; slot = 0; break;
+            case 1: wk = pf::K_E2 + q * 2 + 1; slot = 2; break;
+            default: return false;
+        }
+    } else {
+        switch ((f >> 5) & 3u) {
+            case 3: wk = pf::K_WD + q * 2; p -= 1; slot = 0; break;
+            case 2: wk = pf::K_WD + q * 2 + 1; p -= 1; slot = 1; break;
+            case 1: wk = pf::K_WX + 1; p = c.xd_src_p; slot = c.xd_src_slot; break;
+            default: wk = pf::K_WH + q; p -= 1; break;
+        }
+    }
+    return true;
+}
+
+}  // namespace pq
+}  // namespace strique

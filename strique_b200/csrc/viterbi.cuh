@@ -74,6 +74,10 @@ struct VitProfModelDev {
     int n_end;
     int32_t end_p[16], end_slot[16];
     double end_w[16];
+    // fixed-point image (profile_q.h) when the model fits its bounds, else nullptr: the model then stays on the
+    // float64 kernel
+    const int32_t *qgrp;           // [pq::G_TOTAL][32][4]
+    const double *qem;             // [pq::E_TOTAL][32][2]
 };
 
 struct HmmModel {                 // host-side handle; device arrays owned by the context
@@ -148,6 +152,11 @@ int viterbi_fast_teams(const VitFastShape &shape);   // sequences per CTA task
 int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
 int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta);
 int viterbi_profile_launch(strique_ctx *ctx, const VitProfBatch &b, int grid);
+// fixed-point profile kernel (viterbi_profile_q.cu): same batch layout; sequences it declines come back with status 3
+struct ProfileImage;
+int viterbi_profile_q_pack(strique_ctx *ctx, const ProfileImage &img, VitProfModelDev *f);
+int viterbi_profile_q_max_grid(strique_ctx *ctx, int *warps_per_cta);
+int viterbi_profile_q_launch(strique_ctx *ctx, const VitProfBatch &b, int grid);
 // decodes sequences of several models in one pass: seq_model[s] indexes ctx->models
 int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
                              int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,

@@ -429,7 +429,7 @@ int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *
     f.n_end = img.n_end;
     for (int e = 0; e < img.n_end; ++e) { f.end_p[e] = img.end_p[e]; f.end_slot[e] = img.end_slot[e]; f.end_w[e] = img.end_w[e]; }
     m->has_profile = true;
-    return STRIQUE_OK;
+    return viterbi_profile_q_pack(ctx, img, &f);
 }
 
 }  // namespace strique

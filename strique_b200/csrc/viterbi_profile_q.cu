@@ -1,0 +1,384 @@
+// Fixed-point profile Viterbi: the throughput kernel of boundary #2 for the reference's linear profile HMMs.
+//
+// Replaces pomegranate 0.10.0 `HiddenMarkovModel.viterbi` behind flankedRepeatHMM.count_repeats (reference
+// scripts/STRique.py:433-441, 374-378; topology 201-431).  Same mapping as the float64 kernel
+// (viterbi_profile.cu: one warp per sequence, lane l owns profile positions 4l..4l+3, neighbours by shuffle,
+// delete chain as a max-plus scan, one back-pointer word per lane per column), different arithmetic
+// (profile_q.h): tagged int32 fixed-point scores, so that ONE VIADDMNMX per in-edge relaxes the edge and carries
+// the winner's name -- no compare / select chains, no 64-bit shuffles, half the registers.  The decoded path is
+// re-scored in float64 during the traceback (log p = exact score of the returned path); sequences the fixed-point
+// pass cannot vouch for (samples outside the fast emission range, unreachable END, forward value and re-score
+// disagreeing beyond the quantisation bound) get status 3 and are decoded by the float64 kernel instead.
+#include <math.h>
+
+#include <algorithm>
+
+#include "profile_q_pack.h"
+#include "viterbi.cuh"
+
+namespace strique {
+
+namespace {
+
+#ifndef PROFQ_WARPS_PER_CTA
+#define PROFQ_WARPS_PER_CTA 4
+#endif
+#ifndef PROFQ_CTAS
+#define PROFQ_CTAS 4
+#endif
+constexpr int PROFQ_WARPS = PROFQ_WARPS_PER_CTA;
+constexpr int PROFQ_CTAS_PER_SM = PROFQ_CTAS;
+constexpr int PROFQ_STAGE_ROWS = 32;
+constexpr int PROFQ_GRP_SH = pq::G_TOTAL - pq::P;                  // groups kept in shared memory (G_WM: registers)
+constexpr int PROFQ_TAB_BYTES = PROFQ_GRP_SH * 32 * 16 + pq::E_TOTAL * 32 * 16;
+constexpr int PROFQ_STAGE_BYTES = PROFQ_STAGE_ROWS * 32 * 4;       // per warp: back-pointer rows of the traceback
+static_assert(PROFQ_STAGE_BYTES >= 3 * pf::NPOS * 4, "the END gather reuses the stage area");
+
+struct TabQ {                                                      // this lane's view of the CTA's model table
+    const int4 *g;                                                 // &grp[lane]; group k of lane l at grp[(k - P) * 32 + l]
+    const double2 *e;                                              // &em[lane]
+    __device__ __forceinline__ pq::I4 grp(int k) const {
+        const int4 v = g[(k - pq::P) * 32];
+        return pq::I4{v.x, v.y, v.z, v.w};
+    }
+    __device__ __forceinline__ pf::Pair dpair(int k) const {
+        const double2 v = e[k * 32];
+        return pf::Pair{v.x, v.y};
+    }
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ModelScalars {                                              // warp-uniform
+    int p_start, xlane, xm_slot, xd_slot;
+    double lo, hi;
+};
+
+struct SeqCtx {
+    int seq, T;
+    int64_t xo;
+    const double *x;
+    uint32_t *bp;
+};
+
+__device__ __forceinline__ SeqCtx seq_ctx(const VitProfBatch &b, int seq) {
+    SeqCtx c;
+    c.seq = seq;
+    c.xo = b.x_off[seq];
+    c.T = (int)(b.x_off[seq + 1] - c.xo);
+    c.x = b.x + c.xo;
+    c.bp = b.bp + b.bp_off[seq];
+    return c;
+}
+
+// E1 of the next column + delete chain of the column just finished.
+// XQ = in-lane index of the position that feeds the repeat loop (compile time).
+template <int XQ>
+__device__ __forceinline__ uint32_t block(const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms, pq::StateQ &S) {
+    const int32_t pM3 = __shfl_up_sync(FULL, S.M[3], 1);
+    const int32_t pI3 = __shfl_up_sync(FULL, S.I[3], 1);
+    const int32_t pM2 = __shfl_up_sync(FULL, S.M[2], 1);
+    const int32_t vm = S.M[XQ], vi = S.I[XQ];
+    const int32_t xm = __shfl_sync(FULL, ms.xm_slot ? vi : vm, ms.xlane);
+    const int32_t xd = __shfl_sync(FULL, ms.xd_slot ? vi : vm, ms.xlane);
+    int32_t a[pq::P], A;
+    pq::d_entry(tab, S, pM3, pI3, xd, a, A);
+    pq::e1(R, tab, S, pM3, pI3, pM2, xm);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const int32_t Al = __shfl_up_sync(FULL, A, 1 << r);
+        A = pq::d_round(tab, A, Al, r);
+    }
+    const int32_t Din = __shfl_up_sync(FULL, A, 1);
+    return pq::d_final(tab, S, a, Din);
+}
+
+__device__ __forceinline__ int32_t warp_max(int32_t v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
+// Forward pass of one sequence.  Returns false when a sample lies outside the fast emission range (declined).
+template <int XQ>
+__device__ __forceinline__ bool forward(const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms, const int lane,
+                                        pq::StateQ &S, const SeqCtx &c, long long &off) {
+#pragma unroll
+    for (int q = 0; q < pq::P; ++q) {
+        S.M[q] = (lane * pq::P + q == ms.p_start) ? 0 : pq::Q_NEG;    // START: value 0 before the first sample only
+        S.I[q] = S.D[q] = S.partM[q] = S.partI[q] = pq::Q_NEG;
+    }
+    S.Dprev = pq::Q_NEG;
+    off = 0;
+    c.bp[lane] = block<XQ>(R, tab, ms, S);                            // column 0: delete chain from START
+    double xcur = c.T > 0 ? __ldg(c.x) : 0.0;
+    bool ok = true;
+#pragma unroll 1
+    for (int t = 1; t <= c.T; ++t) {
+        const double xnext = t < c.T ? __ldg(c.x + t) : 0.0;
+        // outside a Uniform range or NaN: the sequence will be declined; the pass runs on (integer arithmetic
+        // cannot trap, nothing of it is used) so that the loop keeps one exit and the warp stays converged
+        ok = ok && (xcur >= ms.lo && xcur <= ms.hi);
+        int32_t eM[pq::P];
+        pq::emissions_q(tab, xcur, eM);
+        const uint32_t word = pq::e2_emit(tab, S, eM);
+        if ((t & (pq::R_NORM - 1)) == 0 || t == 1) {
+            if (t == 1) {
+#pragma unroll
+                for (int q = 0; q < pq::P; ++q)
+                    if (lane * pq::P + q == ms.p_start) S.M[q] = pq::Q_NEG;
+            }
+            const int32_t mx = warp_max(pq::lane_max(S));
+            pq::renorm(S, mx);
+            off += mx;
+        }
+        const uint32_t dbits = block<XQ>(R, tab, ms, S);
+        c.bp[(size_t)t * 32 + lane] = word | dbits;
+        xcur = xnext;
+    }
+    return ok;
+}
+
+// END edges: best (v[T][src] + w), first maximum; unreachable sources do not count
+__device__ __forceinline__ void end_edges(const VitProfModelDev &m, const pq::StateQ &S, uint32_t *stage, const int lane,
+                                          double &best_out, int &barg_out) {
+    const double NINF = pf::ninf();
+    __syncwarp();
+    int32_t *vals = reinterpret_cast<int32_t *>(stage);
+#pragma unroll
+    for (int q = 0; q < pq::P; ++q) {
+        vals[lane * pq::P + q] = S.M[q];
+        vals[pf::NPOS + lane * pq::P + q] = S.I[q];
+        vals[2 * pf::NPOS + lane * pq::P + q] = S.D[q];
+    }
+    __syncwarp();
+    double best = NINF;
+    int barg = -1;
+    if (lane < m.n_end) {
+        const int32_t v = vals[m.end_slot[lane] * pf::NPOS + m.end_p[lane]];
+        if (v >= pq::Q_KILL - pq::R_NORM * pq::S_STEP * pq::Q_ONE) {
+            best = (double)v * (1.0 / (double)pq::Q_ONE) + m.end_w[lane];
+            barg = lane;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_down_sync(FULL, best, off);
+        const int oa = __shfl_down_sync(FULL, barg, off);
+        if (ob > best || (ob == best && oa >= 0 && (barg < 0 || oa < barg))) { best = ob; barg = oa; }
+    }
+    best_out = __shfl_sync(FULL, best, 0);
+    barg_out = __shfl_sync(FULL, barg, 0);
+    __syncwarp();
+}
+
+// Traceback (all lanes walk in lock step; lane 0 / lane i write) with the float64 re-score of the path, and the
+// result record of one sequence.  vfwd = the forward pass's value of the path (relative part + END weight).
+__device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModelDev &m, const SeqCtx &c, uint32_t *stage,
+                                       const int lane, const int p_start, const double vfwd, const int barg) {
+    const int T = c.T;
+    const uint32_t *bp = c.bp;
+    VitResult r;
+    r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 0; r.reserved = 0;
+    double acc = lane == 0 ? m.end_w[barg] : 0.0;
+    const pf::TraceCfg tc = m.trace;
+    int p = m.end_p[barg], slot = m.end_slot[barg], t = T;
+    uint8_t *pat = b.pattern ? b.pattern + c.xo : nullptr;
+    uint16_t *path = b.path ? b.path + c.xo : nullptr;
+    bool in_group = false;
+    uint8_t last_mod = '0';
+    int plen = 0;
+    int stage_lo = T + 1;                 // rows [stage_lo, stage_lo + 32) are staged
+    long long guard = (long long)(T + 2) * (pf::NPOS + 2);
+    while (!(slot == 0 && p == p_start)) {
+        if (--guard < 0 || p < 0 || p >= pf::NPOS || t < 0) { r.status = 2; break; }
+        if (t < stage_lo) {
+            // stage the next rows: 16-byte async copies, all in flight at once
+            __syncwarp();
+            stage_lo = t - (PROFQ_STAGE_ROWS - 1) > 0 ? t - (PROFQ_STAGE_ROWS - 1) : 0;
+            const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)stage_lo * 32);
+            const int nvec = (t - stage_lo + 1) * 8;
+            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage);
+#pragma unroll
+            for (int i = 0; i < PROFQ_STAGE_ROWS * 8 / 32; ++i)
+                if (lane + 32 * i < nvec)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (lane + 32 * i) * 16),
+                                 "l"(src + lane + 32 * i)
+                                 : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+        }
+        const int tl = p >> 2;            // lane that owns the current state: its table column holds the in-edge weights
+        if (slot == 2) {                  // silent delete state: same column
+            int wk = 0;
+            if (!pq::back(stage[(t - stage_lo) * 32 + tl], tc, p, slot, t, wk)) { r.status = 2; break; }
+            if (lane == 0) acc += __ldg(m.tab + wk * 32 + tl);
+            continue;
+        }
+        if (t < 1) { r.status = 2; break; }
+        // Emitting state (p, slot) at column t.  Samples dwell in a state, so most pointers are self loops:
+        // lane i looks at column t - i, the warp skips the whole run of self loops at once and then takes
+        // the first other pointer (all lanes keep the same cursor; lane 0 / lane i write the outputs).
+        const int ti = t - lane;
+        const bool valid = ti >= stage_lo && ti >= 1;
+        const uint32_t wfull = valid ? stage[(ti - stage_lo) * 32 + tl] : 0u;
+        const uint32_t f = wfull >> (8 * (p & 3));
+        const bool self = valid && (slot == 0 ? (f & 7u) == 7u : ((f >> 3) & 3u) == 3u);
+        const unsigned other = ~__ballot_sync(FULL, self);
+        const int k = other ? __ffs(other) - 1 : 32;               // columns t .. t-k+1 are self loops
+        const bool step = k < 32 && ((__ballot_sync(FULL, valid) >> k) & 1u);   // column t-k is staged
+        const int visits = k + (step ? 1 : 0);                     // >= 1: column t itself is staged
+        const int idx = p * 2 + slot;
+        const unsigned fl = m.flags[idx];
+        if (fl & HMM_FLAG_COUNT) r.n_count += visits;
+        if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - visits; }
+        if (fl & HMM_FLAG_SEP) {
+            if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; in_group = false; }
+        } else {
+            in_group = true;
+            last_mod = (fl & HMM_FLAG_MOD) ? '1' : '0';
+        }
+        if (path && lane < visits) path[t - 1 - lane] = (uint16_t)m.state_id[idx];
+        // re-score: lane i adds the emission of column t - i and, inside the run, the self-loop weight
+        if (lane < visits) {
+            acc += pf::emission_slow(m.em_kind[idx], m.em_a[idx], m.em_b[idx], m.em_c[idx], __ldg(c.x + ti - 1));
+            if (lane < k) acc += __ldg(m.tab + (slot == 0 ? pf::K_WMR + (p & 3) * 4 : pf::K_WI + (p & 3) * 2) * 32 + tl);
+        }
+        t -= k;
+        if (step) {
+            const uint32_t w = __shfl_sync(FULL, wfull, k);
+            int wk = 0;
+            if (!pq::back(w, tc, p, slot, t, wk)) { r.status = 2; break; }
+            if (lane == 0) acc += __ldg(m.tab + wk * 32 + tl);
+        }
+    }
+    if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; }
+    if (r.status == 0 && t != 0) r.status = 2;
+    r.pattern_len = plen;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    r.logp = acc;
+    // the forward value of this path and its exact score differ by the rounding of <= 2 addends per column only
+    if (r.status == 0 && !(fabs(vfwd - acc) <= 1.0e-3 + (double)T * (2.0 / (double)(1 << pq::FRAC)))) r.status = 3;
+    if (r.status == 2) r.status = 3;      // let the float64 kernel have the last word
+    if (lane == 0) b.res[c.seq] = r;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void decline(const VitProfBatch &b, const SeqCtx &c, const int lane) {
+    VitResult r;
+    r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 3; r.reserved = 0;
+    if (lane == 0) b.res[c.seq] = r;
+}
+
+// the sequences of one warp in one CTA task
+template <int XQ>
+__device__ __forceinline__ void run_task(const VitProfBatch &b, const VitProfModelDev &m, const VitCtaTask &ct,
+                                         const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms,
+                                         uint32_t *stage, const int lane, const int warp) {
+    if (warp >= ct.count) return;
+    const SeqCtx c = seq_ctx(b, b.order[ct.first + warp]);
+    pq::StateQ S;
+    long long off;
+    if (!forward<XQ>(R, tab, ms, lane, S, c, off)) { decline(b, c, lane); return; }
+    double best;
+    int barg;
+    end_edges(m, S, stage, lane, best, barg);
+    if (barg < 0) { decline(b, c, lane); return; }
+    traceback(b, m, c, stage, lane, ms.p_start, best + (double)off * (1.0 / (double)pq::Q_ONE), barg);
+}
+
+__global__ void __launch_bounds__(PROFQ_WARPS * 32, PROFQ_CTAS_PER_SM) viterbi_profile_q_kernel(VitProfBatch b) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_task;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int4 *grp_s = reinterpret_cast<int4 *>(smem);
+    double2 *em_s = reinterpret_cast<double2 *>(smem + PROFQ_GRP_SH * 32 * 16);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + PROFQ_TAB_BYTES + (size_t)warp * PROFQ_STAGE_BYTES);
+    const TabQ tab{grp_s + lane, em_s + lane};
+
+    int model = -1;
+    pq::RegsQ R;
+    ModelScalars ms{0, 0, 0, 0, 0.0, 0.0};
+    int xq = 0;
+  for (;;) {                            // ---- one CTA task: <= PROFQ_WARPS sequences of one model ----
+    __syncthreads();                                    // everybody is done with s_task and the table
+    if (threadIdx.x == 0) s_task = atomicAdd(b.counters, 1);
+    __syncthreads();
+    if (s_task >= b.n_tasks) return;
+    const VitCtaTask ct = b.tasks[s_task];
+    const VitProfModelDev &m = b.models[ct.model];
+    if (ct.model != model) {
+        model = ct.model;
+        const int4 *gsrc = reinterpret_cast<const int4 *>(m.qgrp);
+        const double2 *esrc = reinterpret_cast<const double2 *>(m.qem);
+        for (int i = threadIdx.x; i < PROFQ_GRP_SH * 32; i += PROFQ_WARPS * 32) grp_s[i] = __ldg(gsrc + pq::P * 32 + i);
+        for (int i = threadIdx.x; i < pq::E_TOTAL * 32; i += PROFQ_WARPS * 32) em_s[i] = __ldg(esrc + i);
+#pragma unroll
+        for (int q = 0; q < pq::P; ++q) {
+            const int4 g = __ldg(gsrc + (pq::G_WM + q) * 32 + lane);
+            R.wM[q][0] = g.x; R.wM[q][1] = g.y; R.wM[q][2] = g.z; R.wM[q][3] = g.w;
+        }
+        ms.p_start = m.p_start;
+        const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+        ms.xlane = xp / pq::P; xq = xp % pq::P;
+        ms.xm_slot = m.trace.xm_src_slot; ms.xd_slot = m.trace.xd_src_slot;
+        ms.lo = m.lo; ms.hi = m.hi;
+        __syncthreads();
+    }
+    switch (xq) {
+        case 0: run_task<0>(b, m, ct, R, tab, ms, stage, lane, warp); break;
+        case 1: run_task<1>(b, m, ct, R, tab, ms, stage, lane, warp); break;
+        case 2: run_task<2>(b, m, ct, R, tab, ms, stage, lane, warp); break;
+        default: run_task<3>(b, m, ct, R, tab, ms, stage, lane, warp); break;
+    }
+  }
+}
+
+}  // namespace
+
+size_t viterbi_profile_q_smem_bytes() { return (size_t)PROFQ_TAB_BYTES + (size_t)PROFQ_WARPS * PROFQ_STAGE_BYTES; }
+
+// Largest useful grid: every resident CTA slot of the device (persistent CTAs pulling from the queue).
+int viterbi_profile_q_max_grid(strique_ctx *ctx, int *warps_per_cta) {
+    static int cached[64] = {0};
+    int &per_sm_cached = cached[ctx->device & 63];
+    if (warps_per_cta) *warps_per_cta = PROFQ_WARPS;
+    if (per_sm_cached == 0) {
+        const size_t smem = viterbi_profile_q_smem_bytes();
+        if (cudaFuncSetAttribute(viterbi_profile_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_profile_q_kernel, PROFQ_WARPS * 32, smem) != cudaSuccess) return 0;
+        per_sm_cached = per_sm < 1 ? 1 : per_sm;
+    }
+    return ctx->num_sms * per_sm_cached;
+}
+
+int viterbi_profile_q_launch(strique_ctx *ctx, const VitProfBatch &b, int grid) {
+    if (grid <= 0) return STRIQUE_OK;
+    viterbi_profile_q_kernel<<<grid, PROFQ_WARPS * 32, viterbi_profile_q_smem_bytes(), ctx->stream>>>(b);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+// Quantises the packed profile image for the fixed-point kernel when it fits the bounds (sets f->qgrp / f->qem).
+int viterbi_profile_q_pack(strique_ctx *ctx, const ProfileImage &img, VitProfModelDev *f) {
+    f->qgrp = nullptr;
+    f->qem = nullptr;
+    ProfileQImage qi;
+    std::string why;
+    if (!profile_quantise(img, &qi, &why)) return STRIQUE_OK;
+    void *pg = nullptr, *pe = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&pg, qi.grp.size() * 4));
+    ctx->owned.push_back(pg);
+    CUDA_TRY(ctx, cudaMalloc(&pe, qi.em.size() * 8));
+    ctx->owned.push_back(pe);
+    CUDA_TRY(ctx, cudaMemcpy(pg, qi.grp.data(), qi.grp.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(pe, qi.em.data(), qi.em.size() * 8, cudaMemcpyHostToDevice));
+    f->qgrp = (const int32_t *)pg;
+    f->qem = (const double *)pe;
+    return STRIQUE_OK;
+}
+
+}  // namespace strique
