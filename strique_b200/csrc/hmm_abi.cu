@@ -238,15 +238,35 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                     if (ctx->models[i]->has_profile) pm[i] = ctx->models[i]->profile; else memset(&pm[i], 0, sizeof(pm[i]));
                 TRY(d_pmodels.ensure(ctx, (size_t)n_models * sizeof(VitProfModelDev)));
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_pmodels.p, pm.data(), pm.size() * sizeof(VitProfModelDev), cudaMemcpyHostToDevice, ctx->stream));
+                DevBuf &d_seqmodel = ctx->buf("vit.seq_model");
+                TRY(d_seqmodel.ensure(ctx, (size_t)n_seq * 4));
+                CUDA_TRY(ctx, cudaMemcpyAsync(d_seqmodel.p, seq_model, (size_t)n_seq * 4, cudaMemcpyHostToDevice, ctx->stream));
                 std::vector<int32_t> order;
                 std::vector<VitCtaTask> ctas;
                 auto run_pass = [&](const std::vector<int32_t> &ids, bool fixed_point) -> int {   // ids in length order
                     if (ids.empty()) return STRIQUE_OK;
+                    VitProfBatch b;
+                    b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
+                    b.n_models = n_models; b.models = d_pmodels.as<VitProfModelDev>();
+                    b.counters = d_queue.as<int>(); b.seq_model = d_seqmodel.as<int32_t>();
+                    b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
+                    b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
+                    CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
+                    if (fixed_point) {
+                        // one warp per sequence, one queue over all models, longest first
+                        int warps_per_cta = 1;
+                        int grid = viterbi_profile_q_max_grid(ctx, &warps_per_cta);
+                        if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi_profile_q_kernel: occupancy query failed");
+                        grid = std::min<int>(grid, ((int)ids.size() + warps_per_cta - 1) / warps_per_cta);
+                        CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                        b.tasks = nullptr; b.n_tasks = (int)ids.size();
+                        return viterbi_profile_q_launch(ctx, b, grid);
+                    }
                     std::vector<std::vector<int32_t>> per_model(n_models);
                     for (int32_t s : ids) per_model[seq_model[s]].push_back(s);
                     int warps_per_cta = 1;
-                    int grid = fixed_point ? viterbi_profile_q_max_grid(ctx, &warps_per_cta) : viterbi_profile_max_grid(ctx, &warps_per_cta);
-                    if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi profile kernel: occupancy query failed");
+                    int grid = viterbi_profile_max_grid(ctx, &warps_per_cta);
+                    if (grid <= 0) FAIL(ctx, STRIQUE_ECUDA, "viterbi_profile_kernel: occupancy query failed");
                     struct HostTask { int model; size_t first; int count; int64_t maxlen; };
                     std::vector<HostTask> tasks;
                     for (int mi = 0; mi < n_models; ++mi)
@@ -262,17 +282,10 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                     }
                     grid = std::min<int>(grid, (int)ctas.size());
                     TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
-                    CUDA_TRY(ctx, cudaMemsetAsync(d_queue.p, 0, 64, ctx->stream));
                     CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
                     CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                    VitProfBatch b;
-                    b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
-                    b.n_models = n_models; b.models = d_pmodels.as<VitProfModelDev>();
-                    b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size(); b.counters = d_queue.as<int>();
-                    b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
-                    b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
-                    if (fixed_point) TRY(viterbi_profile_q_launch(ctx, b, grid)); else TRY(viterbi_profile_launch(ctx, b, grid));
-                    return STRIQUE_OK;
+                    b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size();
+                    return viterbi_profile_launch(ctx, b, grid);
                 };
                 std::vector<int32_t> fixed_ids, exact_ids;
                 for (size_t i = i0; i < i1; ++i) {

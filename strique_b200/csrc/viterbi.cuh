@@ -118,7 +118,8 @@ struct VitProfBatch {
     int n_models;
     const VitProfModelDev *models; // device array indexed by model
     const VitCtaTask *tasks;       // [n_tasks] <= 4 sequences of one model with similar lengths; longest task first
-    int n_tasks;
+    int n_tasks;                   // (fixed-point kernel: one task = one sequence of `order`, its model in seq_model)
+    const int32_t *seq_model;      // [all sequences] model of every sequence
     int *counters;                 // [0]: CTA tasks handed out so far (zeroed by the caller)
     uint32_t *bp;
     const int64_t *bp_off;         // [all sequences] offset in 32-bit words (per sequence: (T+1) * 32 words)

@@ -24,27 +24,22 @@ namespace {
 #define PROFQ_WARPS_PER_CTA 4
 #endif
 #ifndef PROFQ_CTAS
-#define PROFQ_CTAS 4
+#define PROFQ_CTAS 3
 #endif
 constexpr int PROFQ_WARPS = PROFQ_WARPS_PER_CTA;
 constexpr int PROFQ_CTAS_PER_SM = PROFQ_CTAS;
 constexpr int PROFQ_STAGE_ROWS = 32;
-constexpr int PROFQ_GRP_SH = pq::G_TOTAL - pq::P;                  // groups kept in shared memory (G_WM: registers)
-constexpr int PROFQ_TAB_BYTES = PROFQ_GRP_SH * 32 * 16 + pq::E_TOTAL * 32 * 16;
 constexpr int PROFQ_STAGE_BYTES = PROFQ_STAGE_ROWS * 32 * 4;       // per warp: back-pointer rows of the traceback
 static_assert(PROFQ_STAGE_BYTES >= 3 * pf::NPOS * 4, "the END gather reuses the stage area");
 
-struct TabQ {                                                      // this lane's view of the CTA's model table
-    const int4 *g;                                                 // &grp[lane]; group k of lane l at grp[(k - P) * 32 + l]
-    const double2 *e;                                              // &em[lane]
-    __device__ __forceinline__ pq::I4 grp(int k) const {
-        const int4 v = g[(k - pq::P) * 32];
-        return pq::I4{v.x, v.y, v.z, v.w};
-    }
-    __device__ __forceinline__ pf::Pair dpair(int k) const {
-        const double2 v = e[k * 32];
-        return pf::Pair{v.x, v.y};
-    }
+// This lane's constants of the warp's current model, ALL in registers (59 weights, 12 float64 emission constants):
+// the first version kept them in a shared-memory table like the float64 kernel and was bound by the shared-memory
+// pipe (17 LDS.128 = 68 wavefronts per column and warp, 73 % of the pipe with 16 warps per SM, ncu vq_r02a).
+struct TabQ {
+    int32_t g[pq::G_TOTAL][4];
+    double e[pq::E_TOTAL][2];
+    __device__ __forceinline__ pq::I4 grp(int k) const { return pq::I4{g[k][0], g[k][1], g[k][2], g[k][3]}; }
+    __device__ __forceinline__ pf::Pair dpair(int k) const { return pf::Pair{e[k][0], e[k][1]}; }
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -74,7 +69,12 @@ __device__ __forceinline__ SeqCtx seq_ctx(const VitProfBatch &b, int seq) {
 // E1 of the next column + delete chain of the column just finished.
 // XQ = in-lane index of the position that feeds the repeat loop (compile time).
 template <int XQ>
-__device__ __forceinline__ uint32_t block(const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms, pq::StateQ &S) {
+__device__ __forceinline__ uint32_t block(const TabQ &tab, const ModelScalars &ms, pq::StateQ &S) {
+    pq::RegsQ R;
+#pragma unroll
+    for (int q = 0; q < pq::P; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) R.wM[q][k] = tab.g[pq::G_WM + q][k];
     const int32_t pM3 = __shfl_up_sync(FULL, S.M[3], 1);
     const int32_t pI3 = __shfl_up_sync(FULL, S.I[3], 1);
     const int32_t pM2 = __shfl_up_sync(FULL, S.M[2], 1);
@@ -101,7 +101,7 @@ __device__ __forceinline__ int32_t warp_max(int32_t v) {
 
 // Forward pass of one sequence.  Returns false when a sample lies outside the fast emission range (declined).
 template <int XQ>
-__device__ __forceinline__ bool forward(const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms, const int lane,
+__device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms, const int lane,
                                         pq::StateQ &S, const SeqCtx &c, long long &off) {
 #pragma unroll
     for (int q = 0; q < pq::P; ++q) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ bool forward(const pq::RegsQ &R, const TabQ &tab, con
     }
     S.Dprev = pq::Q_NEG;
     off = 0;
-    c.bp[lane] = block<XQ>(R, tab, ms, S);                            // column 0: delete chain from START
+    c.bp[lane] = block<XQ>(tab, ms, S);                            // column 0: delete chain from START
     double xcur = c.T > 0 ? __ldg(c.x) : 0.0;
     bool ok = true;
 #pragma unroll 1
@@ -132,7 +132,7 @@ __device__ __forceinline__ bool forward(const pq::RegsQ &R, const TabQ &tab, con
             pq::renorm(S, mx);
             off += mx;
         }
-        const uint32_t dbits = block<XQ>(R, tab, ms, S);
+        const uint32_t dbits = block<XQ>(tab, ms, S);
         c.bp[(size_t)t * 32 + lane] = word | dbits;
         xcur = xnext;
     }
@@ -271,16 +271,13 @@ __device__ __forceinline__ void decline(const VitProfBatch &b, const SeqCtx &c, 
     if (lane == 0) b.res[c.seq] = r;
 }
 
-// the sequences of one warp in one CTA task
+// one sequence, start to finish, by one warp
 template <int XQ>
-__device__ __forceinline__ void run_task(const VitProfBatch &b, const VitProfModelDev &m, const VitCtaTask &ct,
-                                         const pq::RegsQ &R, const TabQ &tab, const ModelScalars &ms,
-                                         uint32_t *stage, const int lane, const int warp) {
-    if (warp >= ct.count) return;
-    const SeqCtx c = seq_ctx(b, b.order[ct.first + warp]);
+__device__ __forceinline__ void run_seq(const VitProfBatch &b, const VitProfModelDev &m, const SeqCtx &c, const TabQ &tab,
+                                        const ModelScalars &ms, uint32_t *stage, const int lane) {
     pq::StateQ S;
     long long off;
-    if (!forward<XQ>(R, tab, ms, lane, S, c, off)) { decline(b, c, lane); return; }
+    if (!forward<XQ>(tab, ms, lane, S, c, off)) { decline(b, c, lane); return; }
     double best;
     int barg;
     end_edges(m, S, stage, lane, best, barg);
@@ -288,58 +285,60 @@ __device__ __forceinline__ void run_task(const VitProfBatch &b, const VitProfMod
     traceback(b, m, c, stage, lane, ms.p_start, best + (double)off * (1.0 / (double)pq::Q_ONE), barg);
 }
 
+// Persistent warps: every warp pulls whole sequences (longest first, all models of the batch in one queue) and
+// keeps its model's constants in registers until a sequence of another model comes up.  No CTA-level state: the
+// warps of a CTA never wait for each other.
 __global__ void __launch_bounds__(PROFQ_WARPS * 32, PROFQ_CTAS_PER_SM) viterbi_profile_q_kernel(VitProfBatch b) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_task;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int4 *grp_s = reinterpret_cast<int4 *>(smem);
-    double2 *em_s = reinterpret_cast<double2 *>(smem + PROFQ_GRP_SH * 32 * 16);
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + PROFQ_TAB_BYTES + (size_t)warp * PROFQ_STAGE_BYTES);
-    const TabQ tab{grp_s + lane, em_s + lane};
-
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem + (size_t)warp * PROFQ_STAGE_BYTES);
     int model = -1;
-    pq::RegsQ R;
+    TabQ tab;
     ModelScalars ms{0, 0, 0, 0, 0.0, 0.0};
     int xq = 0;
-  for (;;) {                            // ---- one CTA task: <= PROFQ_WARPS sequences of one model ----
-    __syncthreads();                                    // everybody is done with s_task and the table
-    if (threadIdx.x == 0) s_task = atomicAdd(b.counters, 1);
-    __syncthreads();
-    if (s_task >= b.n_tasks) return;
-    const VitCtaTask ct = b.tasks[s_task];
-    const VitProfModelDev &m = b.models[ct.model];
-    if (ct.model != model) {
-        model = ct.model;
-        const int4 *gsrc = reinterpret_cast<const int4 *>(m.qgrp);
-        const double2 *esrc = reinterpret_cast<const double2 *>(m.qem);
-        for (int i = threadIdx.x; i < PROFQ_GRP_SH * 32; i += PROFQ_WARPS * 32) grp_s[i] = __ldg(gsrc + pq::P * 32 + i);
-        for (int i = threadIdx.x; i < pq::E_TOTAL * 32; i += PROFQ_WARPS * 32) em_s[i] = __ldg(esrc + i);
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(b.counters, 1);
+        task = __shfl_sync(FULL, task, 0);
+        if (task >= b.n_tasks) return;
+        const int seq = b.order[task];
+        const int mi = b.seq_model[seq];
+        const VitProfModelDev &m = b.models[mi];
+        if (mi != model) {
+            model = mi;
+            const int4 *gsrc = reinterpret_cast<const int4 *>(m.qgrp);
+            const double2 *esrc = reinterpret_cast<const double2 *>(m.qem);
 #pragma unroll
-        for (int q = 0; q < pq::P; ++q) {
-            const int4 g = __ldg(gsrc + (pq::G_WM + q) * 32 + lane);
-            R.wM[q][0] = g.x; R.wM[q][1] = g.y; R.wM[q][2] = g.z; R.wM[q][3] = g.w;
+            for (int k = 0; k < pq::G_TOTAL; ++k) {
+                const int4 g = __ldg(gsrc + k * 32 + lane);
+                tab.g[k][0] = g.x; tab.g[k][1] = g.y; tab.g[k][2] = g.z; tab.g[k][3] = g.w;
+            }
+#pragma unroll
+            for (int k = 0; k < pq::E_TOTAL; ++k) {
+                const double2 e = __ldg(esrc + k * 32 + lane);
+                tab.e[k][0] = e.x; tab.e[k][1] = e.y;
+            }
+            ms.p_start = m.p_start;
+            const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+            ms.xlane = xp / pq::P; xq = xp % pq::P;
+            ms.xm_slot = m.trace.xm_src_slot; ms.xd_slot = m.trace.xd_src_slot;
+            ms.lo = m.lo; ms.hi = m.hi;
         }
-        ms.p_start = m.p_start;
-        const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
-        ms.xlane = xp / pq::P; xq = xp % pq::P;
-        ms.xm_slot = m.trace.xm_src_slot; ms.xd_slot = m.trace.xd_src_slot;
-        ms.lo = m.lo; ms.hi = m.hi;
-        __syncthreads();
+        const SeqCtx c = seq_ctx(b, seq);
+        switch (xq) {
+            case 0: run_seq<0>(b, m, c, tab, ms, stage, lane); break;
+            case 1: run_seq<1>(b, m, c, tab, ms, stage, lane); break;
+            case 2: run_seq<2>(b, m, c, tab, ms, stage, lane); break;
+            default: run_seq<3>(b, m, c, tab, ms, stage, lane); break;
+        }
     }
-    switch (xq) {
-        case 0: run_task<0>(b, m, ct, R, tab, ms, stage, lane, warp); break;
-        case 1: run_task<1>(b, m, ct, R, tab, ms, stage, lane, warp); break;
-        case 2: run_task<2>(b, m, ct, R, tab, ms, stage, lane, warp); break;
-        default: run_task<3>(b, m, ct, R, tab, ms, stage, lane, warp); break;
-    }
-  }
 }
 
 }  // namespace
 
-size_t viterbi_profile_q_smem_bytes() { return (size_t)PROFQ_TAB_BYTES + (size_t)PROFQ_WARPS * PROFQ_STAGE_BYTES; }
+size_t viterbi_profile_q_smem_bytes() { return (size_t)PROFQ_WARPS * PROFQ_STAGE_BYTES; }
 
-// Largest useful grid: every resident CTA slot of the device (persistent CTAs pulling from the queue).
+// Largest useful grid: every resident CTA slot of the device (persistent warps pulling from the queue).
 int viterbi_profile_q_max_grid(strique_ctx *ctx, int *warps_per_cta) {
     static int cached[64] = {0};
     int &per_sm_cached = cached[ctx->device & 63];
