@@ -61,7 +61,9 @@ enum : int {
     G_EI = G_CWR + 1,         // [q] I-slot emission (Uniform), already shifted: multiple of 8
     G_TOTAL = G_EI + 1
 };
-// ... and float64 emission constants of the M slots, pairs: {mu, 1/(2 sigma^2)}[q], then {c0[0], c0[1]}, {c0[2], c0[3]}
+// ... and float64 emission constants of the M slots.  log N(x; mu, sigma) = c0 - c (x - mu)^2 with c = 1/(2 sigma^2) is
+// evaluated as  C + A x - c x^2  (x^2 once per column): pairs {A = 2 c mu, c}[q], then {C[0], C[1]}, {C[2], C[3]} with
+// C = c0 - c mu^2.  The cancellation costs ~1e-13 nat, eleven orders below the fixed-point resolution.
 enum : int { E_MU = 0, E_C0 = P, E_TOTAL = P + P / 2 };
 
 struct I4 {
@@ -69,6 +71,17 @@ struct I4 {
 };
 
 PF_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+// a * b + c on the FMA pipe (IMAD).  Opaque to the optimiser on the device: it would otherwise fold the
+// "dirty - clean" tag extraction below back into logic operations on the ALU pipe, the pipe that bounds the kernel.
+PF_HD uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#else
+    return a * b + c;
+#endif
+}
 
 struct RegsQ {
     int32_t wM[P][4];
@@ -92,17 +105,26 @@ PF_HD int32_t to_q16(double e) {
 #endif
 }
 
-// Emissions of the M slots for sample x (inside every Uniform range, not NaN): units of 2^-16, clamped.
+PF_HD double fma_rn(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
+// Emission of the M slot of in-lane position q for sample x (inside every Uniform range, not NaN), x2 = x * x:
+// units of 2^-16, clamped.  Two fused multiply-adds and the rounding add.
+template <class Tab>
+PF_HD int32_t emission_q(const Tab &tab, double x, double x2, int q) {
+    const pf::Pair em = tab.dpair(E_MU + q), cc = tab.dpair(E_C0 + q / 2);
+    return imax(to_q16(fma_rn(-em.b, x2, fma_rn(em.a, x, (q & 1) ? cc.b : cc.a))), E_MIN16);
+}
 template <class Tab>
 PF_HD void emissions_q(const Tab &tab, double x, int32_t eM[P]) {
-    const pf::Pair c01 = tab.dpair(E_C0), c23 = tab.dpair(E_C0 + 1);
+    const double x2 = x * x;
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const pf::Pair em = tab.dpair(E_MU + q);
-        const double dx = x - em.a;
-        const double c0 = q == 0 ? c01.a : (q == 1 ? c01.b : (q == 2 ? c23.a : c23.b));
-        eM[q] = imax(to_q16(c0 - (dx * dx) * em.b), E_MIN16);
-    }
+    for (int q = 0; q < P; ++q) eM[q] = emission_q(tab, x, x2, q);
 }
 
 // E2 + emission: finishes column t from the tagged E1 maxima and the delete states of column t-1.
@@ -110,43 +132,49 @@ PF_HD void emissions_q(const Tab &tab, double x, int32_t eM[P]) {
 template <class Tab>
 PF_HD uint32_t e2_emit(const Tab &tab, StateQ &s, const int32_t eM[P]) {
     const I4 ei = tab.grp(G_EI);
-    int32_t bm[P], bi[P];
+    uint32_t dirty = 0u, clean = 0u;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const I4 wb = tab.grp(G_WB + q), wc = tab.grp(G_WC + q);
         const int32_t dsrc = q == 0 ? s.Dprev : s.D[q > 0 ? q - 1 : 0];
-        bm[q] = imax(dsrc + wb.y, s.partM[q]);
-        bi[q] = imax(s.D[q] + wc.x, s.partI[q]);
-        s.M[q] = (bm[q] + eM[q] * 8) & ~TAG_MASK;
+        const int32_t bm = imax(dsrc + wb.y, s.partM[q]);
+        const int32_t bi = imax(s.D[q] + wc.x, s.partI[q]);
         const int32_t eiq = q == 0 ? ei.x : (q == 1 ? ei.y : (q == 2 ? ei.z : ei.w));
-        s.I[q] = (bi[q] + eiq) & ~TAG_MASK;
+        // the emission is a multiple of 8, so the winner's tag survives the add; tag = dirty - clean.  The byte
+        // packing is sum(dirty * 2^k) - sum(clean * 2^k), multiply-adds on the FMA pipe (wrap-around cancels): the
+        // ALU pipe (add-max, logic) is the one this kernel is bound by.
+        const int32_t md = bm + eM[q] * 8, id = bi + eiq;
+        s.M[q] = md & ~TAG_MASK;
+        s.I[q] = id & ~TAG_MASK;
+        dirty = mad_u32((uint32_t)md, 1u << (8 * q), dirty);
+        clean = mad_u32((uint32_t)s.M[q], 1u << (8 * q), clean);
+        dirty = mad_u32((uint32_t)id, 8u << (8 * q), dirty);
+        clean = mad_u32((uint32_t)s.I[q], 8u << (8 * q), clean);
     }
-    uint32_t word = 0u;
-#pragma unroll
-    for (int q = 0; q < P; ++q) word |= ((uint32_t)(bm[q] & 7) | ((uint32_t)(bi[q] & 3) << 3)) << (8 * q);
-    return word;
+    return dirty - clean;
 }
 
 // E1 of the next column from the emitting values of the column just finished (all clean).
 // pM3 / pI3 / pM2: M, I of the last and M of the last-but-one position of the previous lane; xm: X_M source.
 template <class Tab>
+PF_HD void e1_q(const RegsQ &r, const Tab &tab, StateQ &s, int32_t pM3, int32_t pI3, int32_t pM2, int32_t xm, int q) {
+    const I4 wb = tab.grp(G_WB + q);
+    const int32_t m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
+    const int32_t i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
+    const int32_t m2 = q == 0 ? pM2 : (q == 1 ? pM3 : s.M[q > 1 ? q - 2 : 0]);
+    int32_t c = s.M[q] + r.wM[q][0];
+    c = imax(m1 + r.wM[q][1], c);
+    c = imax(i1 + r.wM[q][2], c);
+    c = imax(s.I[q] + r.wM[q][3], c);
+    c = imax(m2 + wb.x, c);
+    if (q == 0) c = imax(xm + tab.grp(G_X).x, c);
+    s.partM[q] = c;
+    s.partI[q] = imax(s.M[q] + wb.w, s.I[q] + wb.z);
+}
+template <class Tab>
 PF_HD void e1(const RegsQ &r, const Tab &tab, StateQ &s, int32_t pM3, int32_t pI3, int32_t pM2, int32_t xm) {
-    const I4 wx = tab.grp(G_X);
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const I4 wb = tab.grp(G_WB + q);
-        const int32_t m1 = q == 0 ? pM3 : s.M[q > 0 ? q - 1 : 0];
-        const int32_t i1 = q == 0 ? pI3 : s.I[q > 0 ? q - 1 : 0];
-        const int32_t m2 = q == 0 ? pM2 : (q == 1 ? pM3 : s.M[q > 1 ? q - 2 : 0]);
-        int32_t c = s.M[q] + r.wM[q][0];
-        c = imax(m1 + r.wM[q][1], c);
-        c = imax(i1 + r.wM[q][2], c);
-        c = imax(s.I[q] + r.wM[q][3], c);
-        c = imax(m2 + wb.x, c);
-        if (q == 0) c = imax(xm + wx.x, c);
-        s.partM[q] = c;
-        s.partI[q] = imax(s.M[q] + wb.w, s.I[q] + wb.z);
-    }
+    for (int q = 0; q < P; ++q) e1_q(r, tab, s, pM3, pI3, pM2, xm, q);
 }
 
 // Delete chain, part 1: tagged entry maxima a[q] of this lane's D states and the lane composite A
@@ -182,18 +210,19 @@ PF_HD int32_t d_round(const Tab &tab, int32_t A, int32_t Al, int r) {
 // Returns the D back-pointer bits of the column.
 template <class Tab>
 PF_HD uint32_t d_final(const Tab &tab, StateQ &s, const int32_t a[P], int32_t Din) {
-    uint32_t bits = 0u;
+    uint32_t dirty = 0u, clean = 0u;
     int32_t D = Din & ~TAG_MASK;
     s.Dprev = D;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const I4 wc = tab.grp(G_WC + q);
         const int32_t c = imax(D + wc.w, a[q]);
-        bits |= (uint32_t)(c & 3) << (8 * q + 5);
         D = c & ~TAG_MASK;
+        dirty = mad_u32((uint32_t)c, 32u << (8 * q), dirty);
+        clean = mad_u32((uint32_t)D, 32u << (8 * q), clean);
         s.D[q] = D;
     }
-    return bits;
+    return dirty - clean;
 }
 
 // Renormalisation: largest emitting value of the lane ...

@@ -54,9 +54,10 @@ inline bool profile_quantise(const ProfileImage &img, ProfileQImage *out, std::s
             // emissions: M slot Normal {mu, 1/(2 sigma^2), c0} (Uniform and unused slots: mu = 0, c = 0, c0), I slot Uniform
             const double c0 = T(pf::K_EC + q * 2, lane), ei = T(pf::K_EC + q * 2 + 1, lane);
             if (c0 > (double)pq::C0_MAX || ei > (double)pq::C0_MAX || c0 < -(double)pq::E_MAX || ei < -(double)pq::E_MAX) ok = false;
-            out->em[((size_t)(pq::E_MU + q) * 32 + lane) * 2 + 0] = T(pf::K_EM + q * 2, lane);
-            out->em[((size_t)(pq::E_MU + q) * 32 + lane) * 2 + 1] = T(pf::K_EM + q * 2 + 1, lane);
-            out->em[((size_t)(pq::E_C0 + q / 2) * 32 + lane) * 2 + (q & 1)] = c0;
+            const double mu = T(pf::K_EM + q * 2, lane), c = T(pf::K_EM + q * 2 + 1, lane);
+            out->em[((size_t)(pq::E_MU + q) * 32 + lane) * 2 + 0] = 2.0 * c * mu;
+            out->em[((size_t)(pq::E_MU + q) * 32 + lane) * 2 + 1] = c;
+            out->em[((size_t)(pq::E_C0 + q / 2) * 32 + lane) * 2 + (q & 1)] = c0 - c * mu * mu;
             G(pq::G_EI, lane)[q] = pq::to_q16(ei) * 8;
         }
         hop_sum[lane] = (int32_t)std::max<int64_t>(hs, pq::Q_ABSENT);

@@ -29,7 +29,7 @@ namespace {
 constexpr int PROFQ_WARPS = PROFQ_WARPS_PER_CTA;
 constexpr int PROFQ_CTAS_PER_SM = PROFQ_CTAS;
 constexpr int PROFQ_STAGE_ROWS = 32;
-constexpr int PROFQ_STAGE_BYTES = PROFQ_STAGE_ROWS * 32 * 4;       // per warp: back-pointer rows of the traceback
+constexpr int PROFQ_STAGE_BYTES = PROFQ_STAGE_ROWS * 32 * 4 + PROFQ_STAGE_ROWS * 8;   // per warp: back-pointer rows of the traceback + their samples
 static_assert(PROFQ_STAGE_BYTES >= 3 * pf::NPOS * 4, "the END gather reuses the stage area");
 
 // This lane's constants of the warp's current model, ALL in registers (59 weights, 12 float64 emission constants):
@@ -66,10 +66,14 @@ __device__ __forceinline__ SeqCtx seq_ctx(const VitProfBatch &b, int seq) {
     return c;
 }
 
-// E1 of the next column + delete chain of the column just finished.
+// E1 of the next column + delete chain of the column just finished + the emissions of the next column.
 // XQ = in-lane index of the position that feeds the repeat loop (compile time).
+// A warp issues in order, so what follows a shuffle in program order waits for it: the E1 relaxations and the
+// float64 emissions -- neither depends on the scan -- are written BETWEEN the rounds of the cross-lane scan, where
+// they cover the shuffle latencies (ptxas keeps this order; it did not hoist them there by itself).
 template <int XQ>
-__device__ __forceinline__ uint32_t block(const TabQ &tab, const ModelScalars &ms, pq::StateQ &S) {
+__device__ __forceinline__ uint32_t block(const TabQ &tab, const ModelScalars &ms, pq::StateQ &S, const double x,
+                                          int32_t (&eM)[pq::P]) {
     pq::RegsQ R;
 #pragma unroll
     for (int q = 0; q < pq::P; ++q)
@@ -77,29 +81,62 @@ __device__ __forceinline__ uint32_t block(const TabQ &tab, const ModelScalars &m
         for (int k = 0; k < 4; ++k) R.wM[q][k] = tab.g[pq::G_WM + q][k];
     const int32_t pM3 = __shfl_up_sync(FULL, S.M[3], 1);
     const int32_t pI3 = __shfl_up_sync(FULL, S.I[3], 1);
-    const int32_t pM2 = __shfl_up_sync(FULL, S.M[2], 1);
     const int32_t vm = S.M[XQ], vi = S.I[XQ];
-    const int32_t xm = __shfl_sync(FULL, ms.xm_slot ? vi : vm, ms.xlane);
     const int32_t xd = __shfl_sync(FULL, ms.xd_slot ? vi : vm, ms.xlane);
+    const int32_t pM2 = __shfl_up_sync(FULL, S.M[2], 1);
+    const int32_t xm = __shfl_sync(FULL, ms.xm_slot ? vi : vm, ms.xlane);
+    const double x2 = x * x;
+    eM[0] = pq::emission_q(tab, x, x2, 0);
     int32_t a[pq::P], A;
     pq::d_entry(tab, S, pM3, pI3, xd, a, A);
-    pq::e1(R, tab, S, pM3, pI3, pM2, xm);
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        const int32_t Al = __shfl_up_sync(FULL, A, 1 << r);
-        A = pq::d_round(tab, A, Al, r);
-    }
+    int32_t Al = __shfl_up_sync(FULL, A, 1);
+    pq::e1_q(R, tab, S, pM3, pI3, pM2, xm, 0);
+    A = pq::d_round(tab, A, Al, 0);
+    Al = __shfl_up_sync(FULL, A, 2);
+    pq::e1_q(R, tab, S, pM3, pI3, pM2, xm, 1);
+    A = pq::d_round(tab, A, Al, 1);
+    Al = __shfl_up_sync(FULL, A, 4);
+    pq::e1_q(R, tab, S, pM3, pI3, pM2, xm, 2);
+    A = pq::d_round(tab, A, Al, 2);
+    Al = __shfl_up_sync(FULL, A, 8);
+    pq::e1_q(R, tab, S, pM3, pI3, pM2, xm, 3);
+    A = pq::d_round(tab, A, Al, 3);
+    Al = __shfl_up_sync(FULL, A, 16);
+    eM[1] = pq::emission_q(tab, x, x2, 1);
+    eM[2] = pq::emission_q(tab, x, x2, 2);
+    A = pq::d_round(tab, A, Al, 4);
     const int32_t Din = __shfl_up_sync(FULL, A, 1);
+    eM[3] = pq::emission_q(tab, x, x2, 3);
     return pq::d_final(tab, S, a, Din);
 }
 
-__device__ __forceinline__ int32_t warp_max(int32_t v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(FULL, v, off));
-    return v;
+__device__ __forceinline__ int32_t warp_max(int32_t v) { return __reduce_max_sync(FULL, v); }   // one REDUX
+
+// One column: delete chain of column t - 1, E1 + emissions + E2 of column t (x = sample t - 1); stores the
+// back-pointer word of column t - 1.
+template <int XQ>
+__device__ __forceinline__ void column(const TabQ &tab, const ModelScalars &ms, pq::StateQ &S, const double x, bool &ok,
+                                       uint32_t &word, uint32_t *&bp) {
+    // outside a Uniform range or NaN: the sequence will be declined; the pass runs on (integer arithmetic cannot
+    // trap, nothing of it is used) so that the loop keeps one exit and the warp stays converged
+    ok = ok && (x >= ms.lo && x <= ms.hi);
+    int32_t eM[pq::P];
+    const uint32_t dbits = block<XQ>(tab, ms, S, x, eM);
+    *bp = word | dbits;
+    bp += 32;
+    word = pq::e2_emit(tab, S, eM);
+}
+
+__device__ __forceinline__ void renormalise(pq::StateQ &S, long long &off) {
+    const int32_t mx = warp_max(pq::lane_max(S));
+    pq::renorm(S, mx);
+    off += mx;
 }
 
 // Forward pass of one sequence.  Returns false when a sample lies outside the fast emission range (declined).
+// Columns 1..4 and the last T mod 4 go one at a time; in between, groups of four columns are unrolled with the
+// renormalisation at the end of the group (no branch), their samples fetched one group ahead: the tag packing, the
+// stores and the emissions of neighbouring columns then overlap with the shuffle latencies of the scan.
 template <int XQ>
 __device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms, const int lane,
                                         pq::StateQ &S, const SeqCtx &c, long long &off) {
@@ -110,32 +147,44 @@ __device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms,
     }
     S.Dprev = pq::Q_NEG;
     off = 0;
-    c.bp[lane] = block<XQ>(tab, ms, S);                            // column 0: delete chain from START
-    double xcur = c.T > 0 ? __ldg(c.x) : 0.0;
+    // the trip count through a warp reduction: its result lives in a uniform register (see the kernel)
+    const int T = __reduce_max_sync(FULL, c.T);
+    const double *__restrict__ x = c.x;
     bool ok = true;
+    uint32_t word = 0u;                                               // M / I back-pointers of the column just finished
+    uint32_t *bp = c.bp + lane;
+    int t = 1;
 #pragma unroll 1
-    for (int t = 1; t <= c.T; ++t) {
-        const double xnext = t < c.T ? __ldg(c.x + t) : 0.0;
-        // outside a Uniform range or NaN: the sequence will be declined; the pass runs on (integer arithmetic
-        // cannot trap, nothing of it is used) so that the loop keeps one exit and the warp stays converged
-        ok = ok && (xcur >= ms.lo && xcur <= ms.hi);
-        int32_t eM[pq::P];
-        pq::emissions_q(tab, xcur, eM);
-        const uint32_t word = pq::e2_emit(tab, S, eM);
-        if ((t & (pq::R_NORM - 1)) == 0 || t == 1) {
-            if (t == 1) {
+    for (; t <= T && t <= pq::R_NORM; ++t) {
+        column<XQ>(tab, ms, S, __ldg(x + t - 1), ok, word, bp);
+        if (t == 1) {                                                 // START does not outlive the first column
 #pragma unroll
-                for (int q = 0; q < pq::P; ++q)
-                    if (lane * pq::P + q == ms.p_start) S.M[q] = pq::Q_NEG;
-            }
-            const int32_t mx = warp_max(pq::lane_max(S));
-            pq::renorm(S, mx);
-            off += mx;
+            for (int q = 0; q < pq::P; ++q)
+                if (lane * pq::P + q == ms.p_start) S.M[q] = pq::Q_NEG;
+            renormalise(S, off);
         }
-        const uint32_t dbits = block<XQ>(tab, ms, S);
-        c.bp[(size_t)t * 32 + lane] = word | dbits;
-        xcur = xnext;
+        if (t == pq::R_NORM) renormalise(S, off);
     }
+    static_assert(pq::R_NORM == 4, "the group loop below is written for four columns");
+    if (t + 3 <= T) {
+        double x0 = __ldg(x + t - 1), x1 = __ldg(x + t), x2 = __ldg(x + t + 1), x3 = __ldg(x + t + 2);
+#pragma unroll 1
+        for (; t + 3 <= T; t += 4) {
+            const bool more = t + 7 <= T;
+            const double n0 = more ? __ldg(x + t + 3) : 0.0, n1 = more ? __ldg(x + t + 4) : 0.0,
+                         n2 = more ? __ldg(x + t + 5) : 0.0, n3 = more ? __ldg(x + t + 6) : 0.0;
+            column<XQ>(tab, ms, S, x0, ok, word, bp);
+            column<XQ>(tab, ms, S, x1, ok, word, bp);
+            column<XQ>(tab, ms, S, x2, ok, word, bp);
+            column<XQ>(tab, ms, S, x3, ok, word, bp);
+            renormalise(S, off);                                      // t + 3 is a multiple of four
+            x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+        }
+    }
+#pragma unroll 1
+    for (; t <= T; ++t) column<XQ>(tab, ms, S, __ldg(x + t - 1), ok, word, bp);
+    int32_t unused[pq::P];
+    *bp = word | block<XQ>(tab, ms, S, 0.0, unused);                  // column T: delete chain (END edges may leave it)
     return ok;
 }
 
@@ -178,6 +227,15 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
                                        const int lane, const int p_start, const double vfwd, const int barg) {
     const int T = c.T;
     const uint32_t *bp = c.bp;
+    // the model's tables: pointers read once (the loop below stores through other pointers, so the compiler would
+    // re-read them from the model record in every iteration -- a second dependent load per table access)
+    const double *__restrict__ tab = m.tab;
+    const uint8_t *__restrict__ em_kind = m.em_kind;
+    const double *__restrict__ em_a = m.em_a, *__restrict__ em_b = m.em_b, *__restrict__ em_c = m.em_c;
+    const uint8_t *__restrict__ flags = m.flags;
+    const int32_t *__restrict__ state_id = m.state_id;
+    const double *__restrict__ xs = c.x;
+    const double *xstage = reinterpret_cast<const double *>(stage + PROFQ_STAGE_ROWS * 32);
     VitResult r;
     r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 0; r.reserved = 0;
     double acc = lane == 0 ? m.end_w[barg] : 0.0;
@@ -205,6 +263,11 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (lane + 32 * i) * 16),
                                  "l"(src + lane + 32 * i)
                                  : "memory");
+            // ... and the sample of every staged row (row ti decodes sample ti - 1): the re-score reads it from here
+            if (stage_lo + lane >= 1 && stage_lo + lane <= t)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + PROFQ_STAGE_ROWS * 128 + lane * 8),
+                             "l"(xs + stage_lo + lane - 1)
+                             : "memory");
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
         }
@@ -212,7 +275,7 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         if (slot == 2) {                  // silent delete state: same column
             int wk = 0;
             if (!pq::back(stage[(t - stage_lo) * 32 + tl], tc, p, slot, t, wk)) { r.status = 2; break; }
-            if (lane == 0) acc += __ldg(m.tab + wk * 32 + tl);
+            if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
             continue;
         }
         if (t < 1) { r.status = 2; break; }
@@ -229,7 +292,12 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         const bool step = k < 32 && ((__ballot_sync(FULL, valid) >> k) & 1u);   // column t-k is staged
         const int visits = k + (step ? 1 : 0);                     // >= 1: column t itself is staged
         const int idx = p * 2 + slot;
-        const unsigned fl = m.flags[idx];
+        // everything that depends on the state only: loads issued together
+        const unsigned fl = __ldg(flags + idx);
+        const int kind = __ldg(em_kind + idx);
+        const double ea = __ldg(em_a + idx), eb = __ldg(em_b + idx), ec = __ldg(em_c + idx);
+        const double wself = __ldg(tab + (slot == 0 ? pf::K_WMR + (p & 3) * 4 : pf::K_WI + (p & 3) * 2) * 32 + tl);
+        const int sid = path ? __ldg(state_id + idx) : 0;
         if (fl & HMM_FLAG_COUNT) r.n_count += visits;
         if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - visits; }
         if (fl & HMM_FLAG_SEP) {
@@ -238,18 +306,18 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
             in_group = true;
             last_mod = (fl & HMM_FLAG_MOD) ? '1' : '0';
         }
-        if (path && lane < visits) path[t - 1 - lane] = (uint16_t)m.state_id[idx];
+        if (path && lane < visits) path[t - 1 - lane] = (uint16_t)sid;
         // re-score: lane i adds the emission of column t - i and, inside the run, the self-loop weight
         if (lane < visits) {
-            acc += pf::emission_slow(m.em_kind[idx], m.em_a[idx], m.em_b[idx], m.em_c[idx], __ldg(c.x + ti - 1));
-            if (lane < k) acc += __ldg(m.tab + (slot == 0 ? pf::K_WMR + (p & 3) * 4 : pf::K_WI + (p & 3) * 2) * 32 + tl);
+            acc += pf::emission_slow(kind, ea, eb, ec, xstage[ti - stage_lo]);
+            if (lane < k) acc += wself;
         }
         t -= k;
         if (step) {
             const uint32_t w = __shfl_sync(FULL, wfull, k);
             int wk = 0;
             if (!pq::back(w, tc, p, slot, t, wk)) { r.status = 2; break; }
-            if (lane == 0) acc += __ldg(m.tab + wk * 32 + tl);
+            if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
         }
     }
     if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; }
@@ -297,12 +365,14 @@ __global__ void __launch_bounds__(PROFQ_WARPS * 32, PROFQ_CTAS_PER_SM) viterbi_p
     ModelScalars ms{0, 0, 0, 0, 0.0, 0.0};
     int xq = 0;
     for (;;) {
+        // warp-uniform values go through a warp reduction (result in a uniform register): ptxas then knows that the
+        // control flow below does not diverge and emits the shuffles of the column loop without divergence checks
         int task = 0;
         if (lane == 0) task = atomicAdd(b.counters, 1);
-        task = __shfl_sync(FULL, task, 0);
+        task = __reduce_max_sync(FULL, task);
         if (task >= b.n_tasks) return;
-        const int seq = b.order[task];
-        const int mi = b.seq_model[seq];
+        const int seq = __reduce_max_sync(FULL, b.order[task]);
+        const int mi = __reduce_max_sync(FULL, b.seq_model[seq]);
         const VitProfModelDev &m = b.models[mi];
         if (mi != model) {
             model = mi;
@@ -320,7 +390,7 @@ __global__ void __launch_bounds__(PROFQ_WARPS * 32, PROFQ_CTAS_PER_SM) viterbi_p
             }
             ms.p_start = m.p_start;
             const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
-            ms.xlane = xp / pq::P; xq = xp % pq::P;
+            ms.xlane = xp / pq::P; xq = __reduce_max_sync(FULL, xp % pq::P);
             ms.xm_slot = m.trace.xm_src_slot; ms.xd_slot = m.trace.xd_src_slot;
             ms.lo = m.lo; ms.hi = m.hi;
         }
