@@ -242,41 +242,40 @@ PF_HD void renorm(StateQ &s, int32_t mx) {
     }
 }
 
-// Traceback of one step. slot: 0 M, 1 I, 2 D.  Emitting states step back one column.  `wk` receives the index
-// (pf::K_* table of the float64 model, lane = position / 4 of the TARGET state) of the weight of the edge taken.
-// Returns false on a pointer that cannot occur.
-PF_HD bool back(uint32_t word, const pf::TraceCfg &c, int &p, int &slot, int &t, int &wk) {
-    const int q = p & 3;
-    const uint32_t f = word >> (8 * q);
-    if (slot == 0) {
-        --t;
-        switch (f & 7u) {
-            case 7: wk = pf::K_WMR + q * 4; break;
-            case 6: wk = pf::K_WMR + q * 4 + 1; p -= 1; break;
-            case 5: wk = pf::K_WMR + q * 4 + 2; p -= 1; slot = 1; break;
-            case 4: wk = pf::K_WMR + q * 4 + 3; slot = 1; break;
-            case 3: wk = pf::K_WM2 + q; p -= 2; break;
-            case 2: wk = pf::K_WX; p = c.xm_src_p; slot = c.xm_src_slot; break;
-            case 1: wk = pf::K_E2 + q * 2; p -= 1; slot = 2; break;
-            default: return false;
-        }
-    } else if (slot == 1) {
-        --t;
-        switch ((f >> 3) & 3u) {
-            case 3: wk = pf::K_WI + q * 2; break;
-            case 2: wk = pf::K_WI + q * 2 + 1; slot = 0; break;
-            case 1: wk = pf::K_E2 + q * 2 + 1; slot = 2; break;
-            default: return false;
-        }
-    } else {
-        switch ((f >> 5) & 3u) {
-            case 3: wk = pf::K_WD + q * 2; p -= 1; slot = 0; break;
-            case 2: wk = pf::K_WD + q * 2 + 1; p -= 1; slot = 1; break;
-            case 1: wk = pf::K_WX + 1; p = c.xd_src_p; slot = c.xd_src_slot; break;
-            default: wk = pf::K_WH + q; p -= 1; break;
-        }
-    }
+// Traceback of one step. slot: 0 M, 1 I, 2 D.  Emitting states step back one column.  One table entry per
+// (slot, tag): bits 0-1 positions to step back, 2-3 new slot, 4-5 long-range source (1 X_M, 2 X_D), 6 valid,
+// 8-15 / 16-19 index of the edge's weight in the float64 table of the model (pf::K_*): base + q * stride, at the
+// lane (= position / 4) of the TARGET state.
+#define PQ_BACK(dp, ns, sp, base, stride) ((dp) | ((ns) << 2) | ((sp) << 4) | 64 | ((base) << 8) | ((stride) << 16))
+#define PQ_BACK_TABLE                                                                                                  \
+    {   /* M: tag 0 cannot occur */ 0,                                                                                  \
+        PQ_BACK(1, 2, 0, pf::K_E2, 2), PQ_BACK(0, 0, 1, pf::K_WX, 0), PQ_BACK(2, 0, 0, pf::K_WM2, 1),                   \
+        PQ_BACK(0, 1, 0, pf::K_WMR + 3, 4), PQ_BACK(1, 1, 0, pf::K_WMR + 2, 4), PQ_BACK(1, 0, 0, pf::K_WMR + 1, 4),     \
+        PQ_BACK(0, 0, 0, pf::K_WMR, 4),                                                                                 \
+        /* I */ 0, PQ_BACK(0, 2, 0, pf::K_E2 + 1, 2), PQ_BACK(0, 0, 0, pf::K_WI + 1, 2), PQ_BACK(0, 1, 0, pf::K_WI, 2), \
+        0, 0, 0, 0,                                                                                                     \
+        /* D */ PQ_BACK(1, 2, 0, pf::K_WH, 1), PQ_BACK(0, 0, 2, pf::K_WX + 1, 0), PQ_BACK(1, 1, 0, pf::K_WD + 1, 2),    \
+        PQ_BACK(1, 0, 0, pf::K_WD, 2), 0, 0, 0, 0 }
+
+// `entry` = table[slot * 8 + tag of (word, p, slot)].  Returns false on a pointer that cannot occur.
+PF_HD int back_index(uint32_t word, int p, int slot) {
+    const uint32_t f = word >> (8 * (p & 3));
+    return slot * 8 + (int)(slot == 0 ? (f & 7u) : ((f >> (slot == 1 ? 3 : 5)) & 3u));
+}
+PF_HD bool back_apply(int entry, const pf::TraceCfg &c, int &p, int &slot, int &t, int &wk) {
+    if (!(entry & 64)) return false;
+    wk = ((entry >> 8) & 255) + (p & 3) * ((entry >> 16) & 15);
+    if (slot < 2) --t;
+    const int sp = (entry >> 4) & 3;
+    const int ns = (entry >> 2) & 3;
+    if (sp == 0) { p -= entry & 3; slot = ns; }
+    else if (sp == 1) { p = c.xm_src_p; slot = c.xm_src_slot; }
+    else { p = c.xd_src_p; slot = c.xd_src_slot; }
     return true;
+}
+PF_HD bool back(uint32_t word, const pf::TraceCfg &c, int &p, int &slot, int &t, int &wk) {
+    const int table[24] = PQ_BACK_TABLE;
+    return back_apply(table[back_index(word, p, slot)], c, p, slot, t, wk);
 }
 
 }  // namespace pq

@@ -78,6 +78,11 @@ struct VitProfModelDev {
     // float64 kernel
     const int32_t *qgrp;           // [pq::G_TOTAL][32][4]
     const double *qem;             // [pq::E_TOTAL][32][2]
+    // its traceback re-scores the path in float64: one record per (position, slot in {M, I}), index position * 2 +
+    // slot: {a, b, c, self-loop weight} with emission = b - (x - a)^2 c (Uniform / unused slot: a = 0, c = 0), and
+    // flags | caller's state id << 16
+    const double *trec;            // [pf::NPOS * 2][4]
+    const uint32_t *tmeta;         // [pf::NPOS * 2]
 };
 
 struct HmmModel {                 // host-side handle; device arrays owned by the context

@@ -29,7 +29,8 @@ namespace {
 constexpr int PROFQ_WARPS = PROFQ_WARPS_PER_CTA;
 constexpr int PROFQ_CTAS_PER_SM = PROFQ_CTAS;
 constexpr int PROFQ_STAGE_ROWS = 32;
-constexpr int PROFQ_STAGE_BYTES = PROFQ_STAGE_ROWS * 32 * 4 + PROFQ_STAGE_ROWS * 8;   // per warp: back-pointer rows of the traceback + their samples
+constexpr int PROFQ_BUF_BYTES = PROFQ_STAGE_ROWS * 32 * 4 + PROFQ_STAGE_ROWS * 8;   // 32 back-pointer rows + their samples
+constexpr int PROFQ_STAGE_BYTES = 2 * PROFQ_BUF_BYTES;            // per warp: two buffers (the traceback prefetches)
 static_assert(PROFQ_STAGE_BYTES >= 3 * pf::NPOS * 4, "the END gather reuses the stage area");
 
 // This lane's constants of the warp's current model, ALL in registers (59 weights, 12 float64 emission constants):
@@ -43,6 +44,8 @@ struct TabQ {
 };
 
 constexpr unsigned FULL = 0xffffffffu;
+
+__constant__ int c_back[24] = PQ_BACK_TABLE;        // traceback decode (profile_q.h)
 
 struct ModelScalars {                                              // warp-uniform
     int p_start, xlane, xm_slot, xd_slot;
@@ -230,12 +233,9 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
     // the model's tables: pointers read once (the loop below stores through other pointers, so the compiler would
     // re-read them from the model record in every iteration -- a second dependent load per table access)
     const double *__restrict__ tab = m.tab;
-    const uint8_t *__restrict__ em_kind = m.em_kind;
-    const double *__restrict__ em_a = m.em_a, *__restrict__ em_b = m.em_b, *__restrict__ em_c = m.em_c;
-    const uint8_t *__restrict__ flags = m.flags;
-    const int32_t *__restrict__ state_id = m.state_id;
+    const double2 *__restrict__ trec = reinterpret_cast<const double2 *>(m.trec);
+    const uint32_t *__restrict__ tmeta = m.tmeta;
     const double *__restrict__ xs = c.x;
-    const double *xstage = reinterpret_cast<const double *>(stage + PROFQ_STAGE_ROWS * 32);
     VitResult r;
     r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 0; r.reserved = 0;
     double acc = lane == 0 ? m.end_w[barg] : 0.0;
@@ -246,35 +246,56 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
     bool in_group = false;
     uint8_t last_mod = '0';
     int plen = 0;
-    int stage_lo = T + 1;                 // rows [stage_lo, stage_lo + 32) are staged
-    long long guard = (long long)(T + 2) * (pf::NPOS + 2);
-    while (!(slot == 0 && p == p_start)) {
-        if (--guard < 0 || p < 0 || p >= pf::NPOS || t < 0) { r.status = 2; break; }
-        if (t < stage_lo) {
-            // stage the next rows: 16-byte async copies, all in flight at once
-            __syncwarp();
-            stage_lo = t - (PROFQ_STAGE_ROWS - 1) > 0 ? t - (PROFQ_STAGE_ROWS - 1) : 0;
-            const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)stage_lo * 32);
-            const int nvec = (t - stage_lo + 1) * 8;
-            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(stage);
+    // Back-pointer rows are staged in aligned blocks of 32 (block B = rows 32 B .. 32 B + 31) with their samples, two
+    // buffers: while the walk is inside block B, block B - 1 is already on its way from HBM (the rows were written
+    // tens of milliseconds ago and are long gone from L2; waiting ~1 us per block was a third of the traceback).
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+    auto issue = [&](int B) {
+        if (B >= 0) {
+            const int r0 = B * PROFQ_STAGE_ROWS;
+            const uint32_t sdst = sbase + (B & 1) * PROFQ_BUF_BYTES;
+            const uint4 *src = reinterpret_cast<const uint4 *>(bp + (size_t)r0 * 32);
+            const int nvec = min(PROFQ_STAGE_ROWS, T + 1 - r0) * 8;
 #pragma unroll
             for (int i = 0; i < PROFQ_STAGE_ROWS * 8 / 32; ++i)
                 if (lane + 32 * i < nvec)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (lane + 32 * i) * 16),
                                  "l"(src + lane + 32 * i)
                                  : "memory");
-            // ... and the sample of every staged row (row ti decodes sample ti - 1): the re-score reads it from here
-            if (stage_lo + lane >= 1 && stage_lo + lane <= t)
+            // the sample of every staged row (row ti decodes sample ti - 1): the re-score reads it from here
+            if (r0 + lane >= 1 && r0 + lane <= T)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + PROFQ_STAGE_ROWS * 128 + lane * 8),
-                             "l"(xs + stage_lo + lane - 1)
+                             "l"(xs + r0 + lane - 1)
                              : "memory");
-            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = T / PROFQ_STAGE_ROWS;
+    __syncwarp();
+    issue(cur);
+    issue(cur - 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    int stage_lo = cur * PROFQ_STAGE_ROWS;    // rows [stage_lo, stage_lo + 32) are readable
+    const uint32_t *rows = stage + (cur & 1) * (PROFQ_BUF_BYTES / 4);
+    const double *xstage = reinterpret_cast<const double *>(rows + PROFQ_STAGE_ROWS * 32);
+    long long guard = (long long)(T + 2) * (pf::NPOS + 2);
+    while (!(slot == 0 && p == p_start)) {
+        if (--guard < 0 || p < 0 || p >= pf::NPOS || t < 0) { r.status = 2; break; }
+        if (t < stage_lo) {
+            __syncwarp();                     // everybody is done with the block above
+            --cur;
+            issue(cur - 1);                   // into the buffer just left
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp();
+            stage_lo = cur * PROFQ_STAGE_ROWS;
+            rows = stage + (cur & 1) * (PROFQ_BUF_BYTES / 4);
+            xstage = reinterpret_cast<const double *>(rows + PROFQ_STAGE_ROWS * 32);
         }
         const int tl = p >> 2;            // lane that owns the current state: its table column holds the in-edge weights
         if (slot == 2) {                  // silent delete state: same column
             int wk = 0;
-            if (!pq::back(stage[(t - stage_lo) * 32 + tl], tc, p, slot, t, wk)) { r.status = 2; break; }
+            if (!pq::back_apply(c_back[pq::back_index(rows[(t - stage_lo) * 32 + tl], p, slot)], tc, p, slot, t, wk)) { r.status = 2; break; }
             if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
             continue;
         }
@@ -284,7 +305,7 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         // the first other pointer (all lanes keep the same cursor; lane 0 / lane i write the outputs).
         const int ti = t - lane;
         const bool valid = ti >= stage_lo && ti >= 1;
-        const uint32_t wfull = valid ? stage[(ti - stage_lo) * 32 + tl] : 0u;
+        const uint32_t wfull = valid ? rows[(ti - stage_lo) * 32 + tl] : 0u;
         const uint32_t f = wfull >> (8 * (p & 3));
         const bool self = valid && (slot == 0 ? (f & 7u) == 7u : ((f >> 3) & 3u) == 3u);
         const unsigned other = ~__ballot_sync(FULL, self);
@@ -293,11 +314,9 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         const int visits = k + (step ? 1 : 0);                     // >= 1: column t itself is staged
         const int idx = p * 2 + slot;
         // everything that depends on the state only: loads issued together
-        const unsigned fl = __ldg(flags + idx);
-        const int kind = __ldg(em_kind + idx);
-        const double ea = __ldg(em_a + idx), eb = __ldg(em_b + idx), ec = __ldg(em_c + idx);
-        const double wself = __ldg(tab + (slot == 0 ? pf::K_WMR + (p & 3) * 4 : pf::K_WI + (p & 3) * 2) * 32 + tl);
-        const int sid = path ? __ldg(state_id + idx) : 0;
+        const double2 ab = __ldg(trec + idx * 2), cw = __ldg(trec + idx * 2 + 1);
+        const unsigned fl = __ldg(tmeta + idx);
+        const int sid = (int)(fl >> 16);
         if (fl & HMM_FLAG_COUNT) r.n_count += visits;
         if (fl & HMM_FLAG_REPEAT) { if (r.t_last < 0) r.t_last = t - 1; r.t_first = t - visits; }
         if (fl & HMM_FLAG_SEP) {
@@ -309,14 +328,16 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         if (path && lane < visits) path[t - 1 - lane] = (uint16_t)sid;
         // re-score: lane i adds the emission of column t - i and, inside the run, the self-loop weight
         if (lane < visits) {
-            acc += pf::emission_slow(kind, ea, eb, ec, xstage[ti - stage_lo]);
-            if (lane < k) acc += wself;
+            // the forward pass has checked that every sample is a number inside all Uniform ranges
+            const double dx = xstage[ti - stage_lo] - ab.x;
+            acc += ab.y - (dx * dx) * cw.x;
+            if (lane < k) acc += cw.y;
         }
         t -= k;
         if (step) {
             const uint32_t w = __shfl_sync(FULL, wfull, k);
             int wk = 0;
-            if (!pq::back(w, tc, p, slot, t, wk)) { r.status = 2; break; }
+            if (!pq::back_apply(c_back[pq::back_index(w, p, slot)], tc, p, slot, t, wk)) { r.status = 2; break; }
             if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
         }
     }
@@ -435,10 +456,32 @@ int viterbi_profile_q_launch(strique_ctx *ctx, const VitProfBatch &b, int grid) 
 int viterbi_profile_q_pack(strique_ctx *ctx, const ProfileImage &img, VitProfModelDev *f) {
     f->qgrp = nullptr;
     f->qem = nullptr;
+    f->trec = nullptr;
+    f->tmeta = nullptr;
     ProfileQImage qi;
     std::string why;
     if (!profile_quantise(img, &qi, &why)) return STRIQUE_OK;
-    void *pg = nullptr, *pe = nullptr;
+    std::vector<double> trec((size_t)pf::NPOS * 2 * 4, 0.0);
+    std::vector<uint32_t> tmeta((size_t)pf::NPOS * 2, 0u);
+    for (int p = 0; p < pf::NPOS; ++p)
+        for (int slot = 0; slot < 2; ++slot) {
+            const int idx = p * 2 + slot, q = p % pf::P, lane = p / pf::P;
+            const bool normal = img.em_kind[idx] == 0, uniform = img.em_kind[idx] == 1;
+            trec[idx * 4 + 0] = normal ? img.em_a[idx] : 0.0;
+            trec[idx * 4 + 1] = normal ? img.em_b[idx] : (uniform ? img.em_c[idx] : 0.0);
+            trec[idx * 4 + 2] = normal ? img.em_c[idx] : 0.0;
+            trec[idx * 4 + 3] = img.tab[(size_t)(slot == 0 ? pf::K_WMR + q * 4 : pf::K_WI + q * 2) * 32 + lane];
+            tmeta[idx] = (uint32_t)img.flags[idx] | ((uint32_t)(img.state_id[idx] & 0xffff) << 16);
+        }
+    void *pg = nullptr, *pe = nullptr, *pt = nullptr, *pm = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&pt, trec.size() * 8));
+    ctx->owned.push_back(pt);
+    CUDA_TRY(ctx, cudaMalloc(&pm, tmeta.size() * 4));
+    ctx->owned.push_back(pm);
+    CUDA_TRY(ctx, cudaMemcpy(pt, trec.data(), trec.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(pm, tmeta.data(), tmeta.size() * 4, cudaMemcpyHostToDevice));
+    f->trec = (const double *)pt;
+    f->tmeta = (const uint32_t *)pm;
     CUDA_TRY(ctx, cudaMalloc(&pg, qi.grp.size() * 4));
     ctx->owned.push_back(pg);
     CUDA_TRY(ctx, cudaMalloc(&pe, qi.em.size() * 8));
