@@ -33,7 +33,12 @@ MOD_MODEL = os.path.join(ROOT, 'models', 'r9_4_450bps_mCpG.model')
 # this design does not execute; it is reported as `frac_survey13` for reference.
 ALIGN_LANE_OPS_AFFINE = 9
 ALIGN_LANE_OPS_LINEAR = 5
-VITERBI_LANE_OPS_PER_EDGE = 3     # 1 DADD + 1 compare + 1 select (fp64)
+# Viterbi: the fixed-point kernel relaxes an in-edge with ONE add-max instruction (VIADDMNMX: the winner's name rides
+# in the low bits of the score) on the integer ALU pipe, 64 lanes per SM.  SURVEY.md section 8d counts 3 lane-ops per
+# edge (add, compare, select) against the 128 fp32 lanes per SM: reported as `frac_survey_fp32`; round 1's float64
+# kernel was rated 3 ops against the 64 float64 lanes: `frac_fp64_convention`, for continuity.
+VITERBI_OPS_PER_EDGE_FIXED = 1
+VITERBI_OPS_PER_EDGE_SURVEY = 3
 
 
 def parse_args():
@@ -50,8 +55,13 @@ def parse_args():
     ap.add_argument('--n-lo', type=int, default=2)
     ap.add_argument('--n-hi', type=int, default=1000)
     ap.add_argument('--mod', action='store_true', help='same as --workload c3')
-    ap.add_argument('--cpu-reads', type=int, default=0, help='reads of the CPU baseline sample (0: one per core, <= 32)')
+    ap.add_argument('--cpu-reads', type=int, default=0, help='reads of the CPU baseline sample (0: four per core, <= 128)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (default, the driver\'s contract): every rank owns a batch; strong: ONE dataset of '
+                         '--dataset reads partitioned over the ranks by cost (strique_b200.sharding), rows gathered on rank 0')
+    ap.add_argument('--dataset', type=int, default=65536, help='reads of the strong-scaling dataset')
+    ap.add_argument('--exact', action='store_true', help='float64 Viterbi only (strique_set_viterbi_exact)')
     args = ap.parse_args()
     if args.mod and args.workload == 'c2':
         args.workload = 'c3'
@@ -81,11 +91,36 @@ def workload_name(args):
             % (args.workload.upper(), loci, n, ' + mCpG methylation HMM' if args.mod else '', args.batch))
 
 
-def make_workload(args, pm, pm_mod, n_reads, seed):
+def make_workload(args, indices, seed):
+    """reads `indices` of the workload with this seed (a pool of processes; identical to workload.make_reads)"""
     from strique_b200 import workload
-    return workload.make_reads(pm, n_reads, seed=seed, loci=args.loci, n_lo=args.n_lo, n_hi=args.n_hi,
-                               pm_mod=pm_mod if args.mod else None, mod_fraction=0.5 if args.mod else 0.0,
-                               fixed_n=args.fixed_n, flank=WORKLOADS[args.workload].get('flank', 1000))
+    return workload.make_reads_parallel(MODEL, MOD_MODEL if args.mod else None, indices, seed=seed, loci=args.loci,
+                                        n_lo=args.n_lo, n_hi=args.n_hi, mod_fraction=0.5 if args.mod else 0.0,
+                                        fixed_n=args.fixed_n, flank=WORKLOADS[args.workload].get('flank', 1000))
+
+
+def bench_config(args, world, raw_bytes=None):
+    """`config` of the JSON line: the same for our arm and for the reference arm"""
+    cfg = {'workload': workload_name(args), 'reads_per_step': args.batch * world,
+           'parallelism': 'reads sharded over %d GPU(s), no collective' % world}
+    if args.scaling == 'strong':
+        cfg['reads_per_step'] = args.dataset
+        cfg['workload'] = cfg['workload'].replace('%d reads per step per GPU' % args.batch,
+                                                  'one dataset of %d reads per step' % args.dataset)
+        cfg['parallelism'] = 'one dataset partitioned over %d GPU(s) by cost (LPT), rows gathered on rank 0' % world
+    cfg['l2'] = 'inputs larger than L2 (several hundred MB of raw samples per GPU per step)'
+    return cfg
+
+
+def traffic_per_unit(kernel):
+    """DRAM bytes per algorithmic unit of a kernel from the committed ncu capture (profiles/traffic.json, written by
+    tools/ncu_traffic.py from an `ncu --set full` report: dram__bytes_read.sum + dram__bytes_write.sum divided by
+    the units of the captured launch) -> (bytes per unit, source) or (None, reason)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))[kernel]
+        return float(t['bytes_per_unit']), '%s (%s, commit %s)' % (t['source'], t['unit'], t.get('commit', '?'))
+    except Exception as e:  # noqa: BLE001
+        return None, 'no capture of this kernel in profiles/traffic.json (%s)' % type(e).__name__
 
 
 def flank_cells(items):
@@ -163,13 +198,17 @@ def _cpu_detect(item):
 
 
 def cpu_kind():
+    """What the CPU arm runs: the reference's own compiled aligner (oracle/_ref, built from /root/reference/src) for the
+    two flank alignments -- > 80 % of its time -- and the oracle's restatement of conditioning / HMM build / float64
+    Viterbi for the rest (pomegranate and scikit-image are not installable here).  'port' when oracle/_ref is absent."""
     from oracle import reference_path as rp
-    return 'reference' if rp.load_pyseqan() is not None else 'port'
+    return 'reference-aligner+restatement' if rp.load_pyseqan() is not None else 'port'
 
 
 class CpuPool(object):
     """Pool of worker processes running the CPU path (the reference's mt_dispatcher pattern,
-    scripts/STRique.py:733-830); the HMMs are built in every worker before timing (S.py:682)."""
+    scripts/STRique.py:733-830: workers pull reads from one queue); the HMMs are built in every worker before
+    timing (S.py:682)."""
 
     def __init__(self, cores, use_mod, warm_item, loci=('c9orf72',)):
         import multiprocessing as mp
@@ -180,42 +219,57 @@ class CpuPool(object):
         self.pool.map(_cpu_detect, [warm_item] * cores, chunksize=1)
 
     def run(self, items):
-        """-> (wall seconds, results)"""
+        """-> (wall seconds, results in input order, summed per-read CPU seconds).  Longest reads first, workers pull
+        one read at a time: no core waits for the slowest read of a fixed share."""
+        order = sorted(range(len(items)), key=lambda k: -len(items[k][1]))
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_detect, items, chunksize=1)
-        return time.perf_counter() - t0, [r[0] for r in res]
+        res = [None] * len(items)
+        cpu_s = 0.0
+        for k, (out, dt) in zip(order, self.pool.imap(_cpu_detect, [items[k] for k in order], chunksize=1)):
+            res[k] = out
+            cpu_s += dt
+        return time.perf_counter() - t0, res, cpu_s
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
+def cpu_sample_size(args, cores):
+    return args.cpu_reads or min(4 * cores, 128)
+
+
 def reference_main(args, rank, world):
-    from strique_b200 import pore_model as pmod, workload
+    """The reference arm: the CPU path on the host cores, on the FIRST reads of rank 0's batch of our arm (same
+    generator, same seed), `config` identical to our arm's."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    pm = pmod.pore_model(MODEL)
-    n_sample = args.cpu_reads or min(cores, 256)
-    pool_reads = make_workload(args, pm, pmod.pore_model(MOD_MODEL) if args.mod else None, n_sample, seed=0)
-    items = [(n, s, st) for n, s, st, _ in pool_reads]
-    times = []
+    n_sample = min(cpu_sample_size(args, cores), args.batch)
+    if args.fixed_n:
+        n_sample = min(n_sample, 2 * cores)                  # long-expansion reads take ~20 s each
+    reads = make_workload(args, range(n_sample), seed=1000)
+    items = [(n, s, st) for n, s, st, _ in reads]
+    times, cpu_total = [], 0.0
     pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])), args.loci)
     for step in range(args.warmup + args.steps):
-        wall, _ = pool.run(items)
+        wall, _, cpu_s = pool.run(items)
         if step >= args.warmup:
             times.append(wall)
+            cpu_total += cpu_s
     pool.close()
     total = sum(times)
     value = n_sample * len(times) / total
     cells = flank_cells(items)
     line = {'impl': 'reference', 'metric': 'reads/s', 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 align / f64 viterbi',
-            'data': 'synthetic', 'config': {'workload': workload_name(args), 'sample_reads_per_step': n_sample},
+            'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+            'dtype': 'f32 align / f64 viterbi', 'data': 'synthetic', 'config': bench_config(args, max(world, 1)),
             'align_gcups': cells * len(times) / total / 1e9,
+            'align_gcups_per_core': cells * len(times) / max(cpu_total, 1e-9) / 1e9,
             'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': min(cores, n_sample), 'kind': cpu_kind(),
-                             'sample': '%d reads of the workload per step, one worker process per core' % n_sample},
+                             'sample': 'each step = the first %d reads of the workload (rank 0, same seed as the GPU arm), '
+                                       'workers pull reads longest first' % n_sample},
             'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -224,6 +278,81 @@ def reference_main(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def init_distributed(local_rank, world):
+    """NCCL process group for the plumbing (barrier, max-over-ranks of the timings); no collective on the data path."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    # NCCL (NCCL_DEBUG=VERSION on the GPU boxes) prints its version banner on stdout when the communicator
+    # is created; the contract is ONE JSON line there, so stdout points at stderr until that has happened
+    import ctypes
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        try:
+            ctypes.CDLL(None).fflush(None)
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+def roofline_block(args, dt, res, stages, cells, edges, clocks, n_sm, steps):
+    """Roofline of the two DP kernels from the live stage timers (CUDA events on the library's stream)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # noqa: BLE001
+        pass
+    sm_mhz = clocks['sm_mhz'] or peaks.get('sm_max_mhz', 1965.0)
+    fp32_peak = n_sm * 128 * sm_mhz * 1e6           # fp32 lane-ops/s at the clock seen under load
+    half_peak = n_sm * 64 * sm_mhz * 1e6            # integer-ALU and float64 lane-ops/s: 64 lanes per SM
+    ran = res['hmm_ran'] == 1
+    t_total = float((res['suffix_end'][ran] - res['prefix_begin'][ran]).sum())      # Viterbi columns per launch
+    scan_s = stages['align_scan'] / 1e3
+    vit_s = stages['viterbi_count'] / 1e3
+    ac = dt.align_config
+    linear = ac['gap_open_h'] == ac['gap_extension_h'] and ac['gap_open_v'] == ac['gap_extension_v']
+    align_ops = ALIGN_LANE_OPS_LINEAR if linear else ALIGN_LANE_OPS_AFFINE
+    scan_cups = cells / scan_s if scan_s > 0 else 0.0
+    vit_eups = edges / vit_s if vit_s > 0 else 0.0
+    vit_ops = VITERBI_OPS_PER_EDGE_SURVEY if args.exact else VITERBI_OPS_PER_EDGE_FIXED
+    kernels = {
+        'align_scan': {'bound': 'alu_issue_fp32', 'achieved': scan_cups * align_ops / 1e12,
+                       'peak': fp32_peak / 1e12, 'unit': 'Tlaneop/s',
+                       'frac': scan_cups * align_ops / fp32_peak, 'ops_per_cell': align_ops,
+                       'frac_survey13': scan_cups * 13 / fp32_peak, 'gcups': scan_cups / 1e9,
+                       'ms_per_step': stages['align_scan'] / steps, 'units_per_launch': cells / steps},
+        'viterbi_count': {'bound': 'alu_issue_fp64' if args.exact else 'alu_issue_int32',
+                          'achieved': vit_eups * vit_ops / 1e12, 'peak': half_peak / 1e12, 'unit': 'Tlaneop/s',
+                          'frac': vit_eups * vit_ops / half_peak, 'ops_per_edge': vit_ops,
+                          'frac_survey_fp32': vit_eups * VITERBI_OPS_PER_EDGE_SURVEY / fp32_peak,
+                          'frac_fp64_convention': vit_eups * VITERBI_OPS_PER_EDGE_SURVEY / half_peak,
+                          'gcups': vit_eups / 1e9, 'ms_per_step': stages['viterbi_count'] / steps,
+                          'units_per_launch': t_total,
+                          # back-pointers: 128 B per column written, 128 B read by the traceback, 8 + 8 B sample
+                          'hbm_GBps': t_total * steps * 272 / max(vit_s, 1e-9) / 1e9,
+                          'hbm_peak_GBps': peaks.get('hbm_gbs')},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
+    roofline = dict(kernels[dom])
+    per_unit, source = traffic_per_unit('viterbi_profile_q' if (dom == 'viterbi_count' and not args.exact) else
+                                        ('viterbi_profile' if dom == 'viterbi_count' else 'align_scan'))
+    roofline.update({'kernel': dom, 'traffic': per_unit * roofline['units_per_launch'] if per_unit is not None else None,
+                     'traffic_source': source,
+                     'peak_source': 'issue peak = N_SM x lanes x SM clock sampled under load (fp32: 128 lanes per SM; '
+                                    'integer ALU and float64: 64 lanes per SM); HBM peak: ' +
+                                    ('measured (MEASURED_PEAKS.json)' if peaks else 'fallback 6650 GB/s')})
+    return roofline, kernels
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -235,40 +364,34 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from strique_b200 import _lib, workload
+    from strique_b200 import _lib, sharding, workload
     from strique_b200.counter import repeatCounter
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the hot path has no CPU fallback')
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        # NCCL (NCCL_DEBUG=VERSION on the GPU boxes) prints its version banner on stdout when the communicator
-        # is created; the contract is ONE JSON line there, so stdout points at stderr until that has happened
-        import ctypes
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            try:
-                ctypes.CDLL(None).fflush(None)
-            except Exception:  # noqa: BLE001
-                pass
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+    init_distributed(local_rank, world)
     ctx = _lib.Context(local_rank)
+    ctx.set_viterbi_exact(args.exact)
     dt = repeatCounter(MODEL, mod_model_file=MOD_MODEL if args.mod else None, context=ctx)
     for name in args.loci:
         dt.add_target(name, *workload.LOCI[name])
     cfg = dt._detect_config()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device('cuda', local_rank))
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.scaling == 'strong':
+        strong_main(args, rank, local_rank, world, ctx, dt, cfg, stream, barrier)
+        return
 
     # ---- this rank's batch ------------------------------------------------------------------------
     t_gen = time.time()
-    reads = make_workload(args, dt.pm, dt.pm_mod, args.batch, seed=1000 + rank)
+    reads = make_workload(args, range(args.batch), seed=1000 + rank)
     tids = np.array([dt._target_id(name, strand) for name, _, strand, _ in reads], dtype=np.int32)
     raw_np, off, kind = _lib.Context._pack_raw([s for _, s, _, _ in reads])
     t_gen = time.time() - t_gen
@@ -276,15 +399,9 @@ def main():
     raw_pinned.numpy()[:] = raw_np
     raw_dev = raw_pinned.cuda()
     torch.cuda.synchronize()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device('cuda', local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def run_steps(n_steps, host_buffers):
-        """-> (device ms, accumulated stage ms, results of the last step)"""
+        """-> (device ms, accumulated stage ms, results of the last step, cells, edges)"""
         stages = {}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -310,6 +427,7 @@ def main():
     launches0 = ctx.launches
     ms, stages, res, cells, edges = run_steps(args.steps, False)
     launches = ctx.launches - launches0
+    fixed, declined = ctx.last_viterbi_fixed
     clocks = sampler.stop()
     run_steps(1, True)
     ms_e2e, _, res_e2e, _, _ = run_steps(args.steps, True)
@@ -335,57 +453,24 @@ def main():
         exact = int((got == truth).sum())
         within1 = int((np.abs(got - truth) <= 1).sum())
         assert np.array_equal(res['count'], res_e2e['count']) and np.array_equal(res['offset'], res_e2e['offset'])
-
-        # ---- roofline of the DP kernels (this rank) ------------------------------------------------
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:  # noqa: BLE001
-            pass
-        sm_mhz = clocks['sm_mhz'] or peaks.get('sm_max_mhz', 1965.0)
-        n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        alu_peak = n_sm * 128 * sm_mhz * 1e6            # fp32 lane-ops/s at the clock seen under load
-        fp64_peak = n_sm * 64 * sm_mhz * 1e6            # fp64 lane-ops/s (B200: 64 DFMA lanes per SM)
-        ran = res['hmm_ran'] == 1
-        t_total = float((res['suffix_end'][ran] - res['prefix_begin'][ran]).sum())
-        scan_s = stages['align_scan'] / 1e3
-        trace_s = stages['align_trace'] / 1e3
-        vit_s = stages['viterbi_count'] / 1e3
-        ac = dt.align_config
-        linear = ac['gap_open_h'] == ac['gap_extension_h'] and ac['gap_open_v'] == ac['gap_extension_v']
-        align_ops = ALIGN_LANE_OPS_LINEAR if linear else ALIGN_LANE_OPS_AFFINE
-        scan_cups = cells / scan_s if scan_s > 0 else 0.0
-        vit_eups = edges / vit_s if vit_s > 0 else 0.0
-        kernels = {
-            'align_scan': {'bound': 'alu_issue_fp32', 'achieved': scan_cups * align_ops / 1e12,
-                           'peak': alu_peak / 1e12, 'unit': 'Tlaneop/s',
-                           'frac': scan_cups * align_ops / alu_peak, 'ops_per_cell': align_ops,
-                           'frac_survey13': scan_cups * 13 / alu_peak, 'gcups': scan_cups / 1e9,
-                           'ms_per_step': stages['align_scan'] / args.steps},
-            'viterbi_count': {'bound': 'alu_issue_fp64', 'achieved': vit_eups * VITERBI_LANE_OPS_PER_EDGE / 1e12,
-                              'peak': fp64_peak / 1e12, 'unit': 'Tlaneop/s',
-                              'frac': vit_eups * VITERBI_LANE_OPS_PER_EDGE / fp64_peak,
-                              'ops_per_edge': VITERBI_LANE_OPS_PER_EDGE, 'gcups': vit_eups / 1e9,
-                              'ms_per_step': stages['viterbi_count'] / args.steps,
-                              # back-pointers: 128 B per time step written, 128 B read by the traceback, 8 B sample
-                              'hbm_GBps': t_total * args.steps * 264 / max(vit_s, 1e-9) / 1e9,
-                              'hbm_peak_GBps': peaks.get('hbm_gbs')},
-        }
-        dom = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
-        roofline = dict(kernels[dom])
-        # DRAM traffic per launch of the dominant kernel, from the ncu --set full capture in profiles/
-        # (viterbi: 251 B per time step measured vs 264 B algorithmic; scan: 0.043 B per cell)
-        traffic = t_total * 251.0 if dom == 'viterbi_count' else (cells / args.steps) * 0.0428
-        roofline.update({'kernel': dom, 'traffic': traffic, 'traffic_source': 'profiles/ncu_*_r01v.txt scaled to this launch',
-                         'peak_source': 'issue peak = N_SM x lanes x SM clock sampled under load (fp32: 128 lanes/SM, '
-                                        'fp64: 64 lanes/SM); HBM peak: ' +
-                                        ('of measured (MEASURED_PEAKS.json)' if peaks else 'of fallback 6650 GB/s')})
+        # ---- the fixed-point Viterbi against the float64 kernel on this very batch (after the timed regions) ----
+        viterbi_check = None
+        if not args.exact:
+            ctx.set_viterbi_exact(True)
+            res64, _ = ctx.detect_batch(cfg, raw_dev.data_ptr(), off, kind, tids, memspace=_lib.DEVICE)
+            ctx.set_viterbi_exact(False)
+            diff = np.flatnonzero((res64['count'] != res['count']) | (res64['hmm_ran'] != res['hmm_ran']))
+            lp = np.abs(res64['log_p'] - res['log_p'])
+            viterbi_check = {'reads': int(len(truth)), 'decoded_fixed_point': int(fixed), 'handed_to_float64': int(declined),
+                             'count_differs_from_float64': int(len(diff)), 'differing_reads': [int(i) for i in diff[:32]],
+                             'max_abs_log_p_gap': float(lp.max()) if len(lp) else 0.0,
+                             'reads_with_log_p_gap_over_1e-9_rel': int((lp > 1e-9 * np.abs(res64['log_p'])).sum())}
+        roofline, kernels = roofline_block(args, dt, res, stages, cells, edges, clocks, n_sm, args.steps)
         line = {'metric': 'reads/s', 'value': value, 'unit': 'reads/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32 align / f64 viterbi', 'data': 'synthetic',
-                'config': {'workload': workload_name(args), 'reads_per_step': args.batch * world,
-                           'l2': 'inputs larger than L2 (%.0f MB raw per GPU per step)' % (raw_np.nbytes / 1e6),
-                           'parallelism': 'reads sharded over %d GPU(s), no collective' % world},
+                'vs_baseline': None,
+                'dtype': 'f32 align / f64 viterbi' if args.exact else 'f32 align / i32 fixed-point viterbi (f64 re-score)',
+                'data': 'synthetic', 'config': bench_config(args, world),
                 'dp_gcups': (cells_all + edges_all) / (ms / 1e3) / 1e9,
                 'align_gcups': cells_all / (ms / 1e3) / 1e9, 'viterbi_gcups': edges_all / (ms / 1e3) / 1e9,
                 'stage_ms_per_step': {k: v / args.steps for k, v in stages.items()},
@@ -395,27 +480,147 @@ def main():
                         'd2h_bytes_per_step': int(res.nbytes) * world},
                 'gpu_launches': int(launches), 'clocks': clocks,
                 'accuracy': {'reads': int(len(truth)), 'count_exact': exact, 'count_within_1': within1},
-                'gen_s': t_gen}
+                'viterbi_check': viterbi_check, 'gen_s': t_gen, 'raw_mb_per_gpu_per_step': raw_np.nbytes / 1e6}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_sample = args.cpu_reads or min(cores, 32)
+            n_sample = min(cpu_sample_size(args, cores), args.batch)
+            if args.fixed_n:
+                n_sample = min(n_sample, cores)
             items = [(n, s, st) for n, s, st, _ in reads[:n_sample]]
             pool = CpuPool(min(cores, n_sample), args.mod, min(items, key=lambda it: len(it[1])), args.loci)
-            wall, cpu_res = pool.run(items)
+            wall, cpu_res, cpu_s = pool.run(items)
             pool.close()
             mism = sum(1 for k in range(n_sample)
                        if (int(cpu_res[k][0]), int(cpu_res[k][4]), int(cpu_res[k][5])) !=
                        (int(res['count'][k]) if res['hmm_ran'][k] else 0, int(res['offset'][k]), int(res['ticks'][k])))
             line['cpu_baseline'] = {'value': n_sample / wall, 'unit': 'reads/s', 'cores': min(cores, n_sample),
                                     'kind': cpu_kind(),
-                                    'sample': 'first %d reads of the step, one worker process per core, %.1f s wall'
+                                    'sample': 'first %d reads of the step, workers pull reads longest first, %.1f s wall'
                                               % (n_sample, wall),
+                                    'align_gcups_per_core': flank_cells(items) / max(cpu_s, 1e-9) / 1e9,
                                     'mismatches_vs_gpu': mism}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
+
+def strong_main(args, rank, local_rank, world, ctx, dt, cfg, stream, barrier):
+    """Strong scaling through the real sharding path (the reference's dispatcher, scripts/STRique.py:733-830, hands
+    reads to workers; here strique_b200.sharding.lpt_partition deals the reads of ONE dataset to the ranks by cost):
+    every rank decodes its shard in batches of --batch reads from pinned host buffers and rank 0 gathers the result
+    rows of all ranks (44 bytes per read, as one byte tensor per rank through the process group) -- all inside the
+    timed region.  Reports per-rank milliseconds and the imbalance."""
+    import torch
+    import torch.distributed as dist
+    from strique_b200 import _lib, sharding
+    n = args.dataset
+    # ---- the dataset: every rank makes a strided slice to learn the read lengths, the lengths are all-gathered, every
+    # rank computes the same partition and then makes the reads it was dealt (reads are individually seeded)
+    t_gen = time.time()
+    mine = list(range(rank, n, world))
+    part = make_workload(args, mine, seed=4000)
+    lens = torch.zeros(n, dtype=torch.int64, device='cuda')
+    lens[torch.tensor(mine, device='cuda')] = torch.tensor([len(s) for _, s, _, _ in part], device='cuda')
+    if world > 1:
+        dist.all_reduce(lens, op=dist.ReduceOp.SUM)
+    lens = lens.cpu().numpy()
+    shards = sharding.lpt_partition([int(x) for x in lens], world)
+    have = dict(zip(mine, part))
+    need = [i for i in shards[rank] if i not in have]
+    have.update(zip(need, make_workload(args, need, seed=4000) if need else []))
+    reads = [have[i] for i in shards[rank]]
+    del have, part
+    t_gen = time.time() - t_gen
+    # batches of --batch reads, pinned
+    batches = []
+    for b0 in range(0, len(reads), args.batch):
+        chunk = reads[b0:b0 + args.batch]
+        tids = np.array([dt._target_id(name, strand) for name, _, strand, _ in chunk], dtype=np.int32)
+        raw_np, off, kind = _lib.Context._pack_raw([s for _, s, _, _ in chunk])
+        pinned = torch.empty(len(raw_np), dtype=torch.int16).pin_memory()
+        pinned.numpy()[:] = raw_np
+        batches.append((pinned, off, kind, tids))
+    row_dtype = np.dtype([('index', np.int64), ('count', np.int32), ('offset', np.int32), ('ticks', np.int32),
+                          ('score_prefix', np.float64), ('score_suffix', np.float64), ('log_p', np.float64)])
+
+    def one_pass():
+        rows = np.zeros(len(reads), dtype=row_dtype)
+        rows['index'] = shards[rank]
+        k = 0
+        for pinned, off, kind, tids in batches:
+            res, _ = ctx.detect_batch(cfg, pinned.numpy(), off, kind, tids, memspace=_lib.HOST)
+            m = len(tids)
+            for f in ('count', 'offset', 'ticks', 'score_prefix', 'score_suffix', 'log_p'):
+                rows[f][k:k + m] = res[f]
+            k += m
+        # host-side gather of the rows on rank 0 (44 bytes per read), in input order
+        if world > 1:
+            sizes = [len(s) for s in shards]
+            cap = max(sizes) * row_dtype.itemsize                 # gather wants equal sizes: pad to the largest shard
+            mine_t = torch.zeros(cap, dtype=torch.uint8, device='cuda')
+            mine_t[:rows.nbytes] = torch.from_numpy(rows.view(np.uint8).copy()).cuda()
+            if rank == 0:
+                parts = [torch.empty(cap, dtype=torch.uint8, device='cuda') for _ in sizes]
+                dist.gather(mine_t, parts, dst=0)
+                allrows = np.concatenate([p.cpu().numpy()[:sz * row_dtype.itemsize].view(row_dtype)
+                                          for p, sz in zip(parts, sizes)])
+            else:
+                dist.gather(mine_t, None, dst=0)
+                allrows = None
+        else:
+            allrows = rows
+        if allrows is not None:
+            allrows = allrows[np.argsort(allrows['index'], kind='stable')]
+        return allrows
+
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    launches0 = ctx.launches
+    my_ms = 0.0
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        allrows = one_pass()
+        my_ms += (time.perf_counter() - t1) * 1e3
+    ev1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    per_rank = torch.zeros(world, dtype=torch.float64, device='cuda')
+    per_rank[rank] = my_ms / args.steps
+    t = torch.tensor([max(dev_ms, wall_ms)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    ms = float(t[0])
+    per_rank = [float(x) for x in per_rank.cpu()]
+    if rank == 0:
+        assert len(allrows) == n and np.array_equal(allrows['index'], np.arange(n))
+        value = n * args.steps / (ms / 1e3)
+        samples = [int(lens[s].sum()) for s in shards]
+        line = {'metric': 'reads/s', 'value': value, 'unit': 'reads/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f32 align / i32 fixed-point viterbi (f64 re-score)', 'data': 'synthetic',
+                'config': bench_config(args, world),
+                'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': int(lens.sum()) * 2,
+                        'd2h_bytes_per_step': n * row_dtype.itemsize},
+                'per_rank_ms': per_rank, 'imbalance_max_over_mean': max(per_rank) / (sum(per_rank) / len(per_rank)),
+                'per_rank_samples': samples, 'batches_per_rank': len(batches), 'gpu_launches': int(launches),
+                'clocks': clocks, 'gen_s': t_gen,
+                'note': 'timed region = every rank: detect_batch over its shard from pinned host buffers + gather of the '
+                        'rows on rank 0; value = dataset reads / max over ranks'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

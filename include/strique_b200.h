@@ -35,6 +35,7 @@ extern "C" {
 #define STRIQUE_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
 #define STRIQUE_ENOMEM (-3)   /* device or host allocation failed */
 #define STRIQUE_EUNSUPPORTED (-4)
+#define STRIQUE_ENOSPC (-5)   /* an output buffer is too small; the call says which and how many bytes it needs */
 
 #define STRIQUE_HOST 0
 #define STRIQUE_DEVICE 1
@@ -158,9 +159,9 @@ typedef struct {
 } strique_viterbi_result;
 
 int strique_hmm_create(strique_ctx *ctx, const strique_hmm_desc *desc, int32_t *model_id);
-/* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, 4000 = profile kernel
- * (4 positions per lane), 32 = small-model kernel (one state per lane, values in registers), otherwise the team kernel shape as wps*1000 + high_slots*100 + low_slots*10 +
- * chain_slots (diagnostic) */
+/* which Viterbi kernel serves the model: 0 = generic warp-per-sequence kernel, 4000 = profile kernels
+ * (4 positions per lane; fixed point with float64 fallback), 32 = small-model kernel (one state per lane, values in
+ * registers) (diagnostic) */
 int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id);
 /*
  *   x, x_offsets : float64 samples of all sequences concatenated; [n_seq+1] offsets (host)
@@ -247,11 +248,14 @@ typedef struct {
 
 /*
  * raw / raw_offsets as in strique_condition_batch; read_target[r] = id from strique_target_create.
- * mod_out (host, capacity mod_cap bytes) receives the '0'/'1' patterns back to back.
+ * mod_out (host, capacity mod_cap bytes) receives the '0'/'1' patterns back to back.  When it is too small the call
+ * returns STRIQUE_ENOSPC and strique_last_mod_bytes() the size that is needed (one pattern character per repeat pass).
  */
 int strique_detect_batch(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
                          int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
                          strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap);
+
+int64_t strique_last_mod_bytes(const strique_ctx *ctx);
 
 /* device time of the stages of the last strique_detect_batch call (ms) */
 #define STRIQUE_STAGE_CONDITION 0

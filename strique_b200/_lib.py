@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('STRIQUE_LIB') or os.path.join(_HERE, 'libstrique_b200.so')
 
 HOST, DEVICE = 0, 1
+ENOSPC = -5      # STRIQUE_ENOSPC: an output buffer was too small
 
 
 class StriqueError(RuntimeError):
@@ -127,6 +128,8 @@ def load():
     lib.strique_last_viterbi_declined.argtypes = [c_void_p]
     lib.strique_set_viterbi_exact.restype = c_int
     lib.strique_set_viterbi_exact.argtypes = [c_void_p, c_int]
+    lib.strique_last_mod_bytes.restype = c_int64
+    lib.strique_last_mod_bytes.argtypes = [c_void_p]
     lib.strique_last_stage_ms.restype = ctypes.c_float
     lib.strique_last_stage_ms.argtypes = [c_void_p, c_int]
     lib.strique_hmm_create.restype = c_int
@@ -309,11 +312,18 @@ class Context:
         read_target = np.ascontiguousarray(read_target, dtype=np.int32)
         n = len(read_target)
         res = np.zeros(n, dtype=DETECT_RESULT_DTYPE)
+        # one pattern character per repeat pass; a pass decodes at least ~3 samples per k-mer of the unit, so this is
+        # generous for real reads -- and when it is not, the library says how much it needs (STRIQUE_ENOSPC)
         cap = int(raw_offsets[-1] // 8 + 64 * n + 64) if cfg.use_mod else 0
-        mod = np.zeros(max(cap, 1), dtype=np.uint8)
-        self.check(self.lib.strique_detect_batch(self.handle, ctypes.byref(cfg), n, _ptr(raw), raw_kind, _ptr(raw_offsets),
-                                                 _ptr(read_target), memspace, _ptr(res), _ptr(mod), cap),
-                   'strique_detect_batch')
+        for attempt in (0, 1):
+            mod = np.zeros(max(cap, 1), dtype=np.uint8)
+            rc = self.lib.strique_detect_batch(self.handle, ctypes.byref(cfg), n, _ptr(raw), raw_kind, _ptr(raw_offsets),
+                                               _ptr(read_target), memspace, _ptr(res), _ptr(mod), cap)
+            if rc == ENOSPC and attempt == 0:
+                cap = int(self.lib.strique_last_mod_bytes(self.handle)) + 64
+                continue
+            self.check(rc, 'strique_detect_batch')
+            break
         return res, mod
 
     def stage_ms(self):

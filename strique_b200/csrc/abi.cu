@@ -13,12 +13,9 @@ std::string g_strique_create_error;
 strique_ctx::~strique_ctx() {
     for (auto &kv : bufs)
         if (kv.second.p) cudaFree(kv.second.p);
-    if (helper) { delete helper; helper = nullptr; }
-    if (!is_helper) {
-        for (void *p : owned) cudaFree(p);
-        for (auto *m : models) delete m;
-        for (auto *t : targets) delete t;
-    }
+    for (void *p : owned) cudaFree(p);
+    for (auto *m : models) delete m;
+    for (auto *t : targets) delete t;
     for (auto &e : stage_ev)
         if (e) cudaEventDestroy(e);
     if (ev0) cudaEventDestroy(ev0);
@@ -28,7 +25,7 @@ strique_ctx::~strique_ctx() {
     for (cudaEvent_t e : copy_ev) if (e) cudaEventDestroy(e);
 }
 
-extern "C" int strique_version(void) { return 100; }
+extern "C" int strique_version(void) { return 200; }
 
 extern "C" int strique_ctx_create(int device, strique_ctx **out) {
     if (!out) return STRIQUE_EINVAL;

@@ -57,10 +57,7 @@ struct strique_ctx {
     std::vector<strique::HmmModel *> models;
     std::vector<strique::Target *> targets;
     std::map<std::string, DevBuf> bufs;   // persistent device scratch
-    // second batch in flight (pipeline.cu): a helper context with its own stream and scratch that shares this
-    // context's models and targets; is_helper contexts do not own them
-    strique_ctx *helper = nullptr;
-    bool is_helper = false;
+    int64_t last_mod_bytes = 0;           // bytes of methylation patterns the last detect call produced / needs
     // cudaMemGetInfo is a driver round trip that was measured at 16 ... 65 ms per call on some (virtualised) GPU
     // boxes: the free-memory figure behind the chunking budgets is cached and refreshed only after an allocation
     size_t free_cached = 0, total_cached = 0;

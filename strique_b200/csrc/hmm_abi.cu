@@ -80,8 +80,8 @@ int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out) {
             continue;
         }
         const int l = perm[p];
-        // candidate order = the team kernel's (viterbi_fast.cu): the self loop, then the other edges
-        // from emitting states / START, then the edges from chain states (stable within each class)
+        // candidate order: the self loop, then the other edges from emitting states / START, then the edges from
+        // chain states (stable within each class)
         int k = 0;
         for (int pass = 0; pass < 3; ++pass)
             for (int e = d->in_ptr[l]; e < d->in_ptr[l + 1]; ++e) {
@@ -145,13 +145,12 @@ int hmm_create(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *out) {
     ctx->owned.push_back(dperm);
     m.blob = (const unsigned char *)dblob;
     m.perm = (const int32_t *)dperm;
-    TRY(viterbi_fast_pack(ctx, d, out));
     return viterbi_profile_pack(ctx, d, out);
 }
 
 // Decodes n_seq device-resident sequences, sequence s with model ctx->models[seq_model[s]].
-// Sequences whose model has a team-kernel image are decoded together per kernel shape (one launch
-// serves both strands / all loci); the rest go through the generic kernel model by model.
+// Sequences of linear profile models (every count model of the reference) are decoded together, one launch for
+// both strands / all loci; the rest go model by model through the small-model kernel or the generic kernel.
 int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const double *x_dev, const int64_t *x_off_host,
                              int n_seq, strique_viterbi_result *results_host, uint8_t *pattern_host,
                              uint16_t *path_host) {
@@ -166,8 +165,7 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     }
     DevBuf &d_xoff = ctx->buf("vit.xoff"), &d_order = ctx->buf("vit.order"), &d_bpoff = ctx->buf("vit.bpoff"),
            &d_bp = ctx->buf("vit.bp"), &d_res = ctx->buf("vit.res"), &d_pat = ctx->buf("vit.pattern"),
-           &d_path = ctx->buf("vit.path"), &d_queue = ctx->buf("vit.queue"), &d_tasks = ctx->buf("vit.tasks"),
-           &d_models = ctx->buf("vit.models");
+           &d_path = ctx->buf("vit.path"), &d_queue = ctx->buf("vit.queue"), &d_tasks = ctx->buf("vit.tasks");
     TRY(d_xoff.ensure(ctx, (size_t)(n_seq + 1) * 8));
     TRY(d_res.ensure(ctx, (size_t)n_seq * sizeof(VitResult)));
     TRY(d_pat.ensure(ctx, std::max<int64_t>(total, 16)));
@@ -176,39 +174,31 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
     TRY(d_bpoff.ensure(ctx, (size_t)n_seq * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_xoff.p, x_off_host, (size_t)(n_seq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     auto len = [&](int s) { return x_off_host[s + 1] - x_off_host[s]; };
-    // STRIQUE_VITERBI_GENERIC / STRIQUE_VITERBI_TEAM force the generic / the team kernel (A/B parity tests)
+    // STRIQUE_VITERBI_GENERIC forces the generic kernel (A/B parity tests)
     const bool force_generic = getenv("STRIQUE_VITERBI_GENERIC") != nullptr;
-    const bool force_team = getenv("STRIQUE_VITERBI_TEAM") != nullptr;
     // STRIQUE_VITERBI_EXACT: float64 kernel only (the fixed-point kernel is the default for models inside its bounds)
     const bool exact_only = getenv("STRIQUE_VITERBI_EXACT") != nullptr || ctx->viterbi_exact;
-    // ---- groups: all profile-kernel models, one per team-kernel shape, one per model for the generic kernel
-    struct Group { bool fast; VitFastShape shape; int model; bool profile; std::vector<int32_t> ids; };
+    // ---- groups: all profile-kernel models together, one group per model otherwise
+    struct Group { int model; bool profile; std::vector<int32_t> ids; };
     std::vector<Group> groups;
     for (int s = 0; s < n_seq; ++s) {
         const HmmModel &m = *ctx->models[seq_model[s]];
-        const bool profile = m.has_profile && !force_generic && !force_team;
-        const bool small = !profile && !force_generic && !force_team && viterbi_small_fits(m.dev);
-        const bool fast = !profile && !small && m.shape.wps > 0 && !force_generic;
+        const bool profile = m.has_profile && !force_generic;
         Group *g = nullptr;
         for (Group &c : groups)
-            if (c.profile == profile && c.fast == fast &&
-                (profile || (fast ? c.shape == m.shape : c.model == seq_model[s]))) { g = &c; break; }
-        if (!g) { groups.push_back(Group{fast, m.shape, seq_model[s], profile, {}}); g = &groups.back(); }
+            if (c.profile == profile && (profile || c.model == seq_model[s])) { g = &c; break; }
+        if (!g) { groups.push_back(Group{seq_model[s], profile, {}}); g = &groups.back(); }
         g->ids.push_back(s);
         ctx->last_viterbi_edges += len(s) * m.n_edges;
     }
-    std::vector<VitFastModelDev> fast_models(n_models);
-    for (int i = 0; i < n_models; ++i) fast_models[i] = ctx->models[i]->fast;
-    TRY(d_models.ensure(ctx, (size_t)n_models * sizeof(VitFastModelDev)));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_models.p, fast_models.data(), (size_t)n_models * sizeof(VitFastModelDev), cudaMemcpyHostToDevice, ctx->stream));
     size_t free_b = 0, total_b = 0;
     { HostTimer ht("vit cudaMemGetInfo"); CUDA_TRY(ctx, ctx_mem_info(ctx, &free_b, &total_b)); }
     const int64_t budget_bytes = (int64_t)std::max<size_t>((size_t)2 << 30, (size_t)((free_b + d_bp.cap) * 0.7));
     std::vector<int64_t> bpoff(n_seq, 0);
     for (Group &g : groups) {
         std::stable_sort(g.ids.begin(), g.ids.end(), [&](int a, int b) { return len(a) > len(b); });
-        const int64_t unit = (g.fast || g.profile) ? 4 : 8;                // bytes per back-pointer word
-        const int64_t words_per_step = g.fast ? g.shape.wps * 32 : 32;
+        const int64_t unit = g.profile ? 4 : 8;                            // bytes per back-pointer word
+        const int64_t words_per_step = 32;
         size_t i0 = 0;
         while (i0 < g.ids.size()) {
             size_t i1 = i0;
@@ -310,55 +300,17 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                     TRY(run_pass(exact_ids, false));
                     { HostTimer ht("vit profile kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }   // host vectors are read by the async copies
                 }
-            } else if (!g.fast) {
+            } else {
                 CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, g.ids.data() + i0, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
                 VitBatch b;
                 b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.n_seq = n; b.order = d_order.as<int32_t>();
                 b.bp = d_bp.as<unsigned long long>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
                 b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
                 b.queue = d_queue.as<int>();
-                if (!force_generic && !force_team && viterbi_small_fits(ctx->models[g.model]->dev))
+                if (!force_generic && viterbi_small_fits(ctx->models[g.model]->dev))
                     TRY(viterbi_small_launch(ctx, *ctx->models[g.model], b));
                 else
                     TRY(viterbi_launch(ctx, *ctx->models[g.model], b));
-            } else {
-                // CTA tasks: per model, runs of `teams` consecutive (length-sorted) sequences; longest task first
-                const int teams = viterbi_fast_teams(g.shape);
-                std::vector<std::vector<int32_t>> per_model(n_models);
-                for (size_t i = i0; i < i1; ++i) per_model[seq_model[g.ids[i]]].push_back(g.ids[i]);
-                struct HostTask { int model; std::vector<int32_t> ids; int64_t maxlen; };
-                std::vector<HostTask> tasks;
-                int blob_cap = 0;
-                for (int mi = 0; mi < n_models; ++mi) {
-                    const auto &v = per_model[mi];
-                    if (v.empty()) continue;
-                    blob_cap = std::max(blob_cap, (int)align_up(ctx->models[mi]->fast.blob_bytes, 16));
-                    for (size_t k = 0; k < v.size(); k += teams) {
-                        HostTask t;
-                        t.model = mi;
-                        t.ids.assign(v.begin() + k, v.begin() + std::min(v.size(), k + teams));
-                        t.maxlen = len(t.ids[0]);
-                        tasks.push_back(std::move(t));
-                    }
-                }
-                std::stable_sort(tasks.begin(), tasks.end(), [](const HostTask &a, const HostTask &b) { return a.maxlen > b.maxlen; });
-                std::vector<int32_t> order;
-                std::vector<VitCtaTask> ctas;
-                for (const HostTask &t : tasks) {
-                    ctas.push_back(VitCtaTask{t.model, (int32_t)order.size(), (int32_t)t.ids.size()});
-                    order.insert(order.end(), t.ids.begin(), t.ids.end());
-                }
-                TRY(d_tasks.ensure(ctx, ctas.size() * sizeof(VitCtaTask)));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                CUDA_TRY(ctx, cudaMemcpyAsync(d_tasks.p, ctas.data(), ctas.size() * sizeof(VitCtaTask), cudaMemcpyHostToDevice, ctx->stream));
-                VitFastBatch b;
-                b.x = x_dev; b.x_off = d_xoff.as<int64_t>(); b.order = d_order.as<int32_t>();
-                b.tasks = d_tasks.as<VitCtaTask>(); b.n_tasks = (int)ctas.size();
-                b.models = d_models.as<VitFastModelDev>(); b.blob_cap = blob_cap;
-                b.bp = d_bp.as<uint32_t>(); b.bp_off = d_bpoff.as<int64_t>(); b.res = d_res.as<VitResult>();
-                b.pattern = d_pat.as<uint8_t>(); b.path = path_host ? d_path.as<uint16_t>() : nullptr;
-                b.queue = d_queue.as<int>();
-                TRY(viterbi_fast_launch(ctx, g.shape, b));
             }
             // host vectors above are read by the async copies: drain before they go out of scope
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -392,8 +344,7 @@ extern "C" int strique_hmm_kernel_shape(const strique_ctx *ctx, int32_t model_id
     if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size()) return -1;
     if (ctx->models[model_id]->has_profile) return 4000;
     if (viterbi_small_fits(ctx->models[model_id]->dev)) return 32;
-    const VitFastShape &s = ctx->models[model_id]->shape;
-    return s.wps * 1000 + s.nh * 100 + s.nl * 10 + s.qc;
+    return 0;
 }
 
 extern "C" int strique_viterbi_batch(strique_ctx *ctx, int32_t model_id, int n_seq, const double *x,

@@ -5,7 +5,6 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "pipeline.cuh"
@@ -88,12 +87,12 @@ static int stage_condition(strique_ctx *ctx, const strique_pore_constants &pore,
 using namespace strique;
 
 extern "C" int64_t strique_last_viterbi_edges(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_edges : 0; }
+extern "C" int64_t strique_last_mod_bytes(const strique_ctx *ctx) { return ctx ? ctx->last_mod_bytes : 0; }
 extern "C" int64_t strique_last_viterbi_fixed(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_fixed : 0; }
 extern "C" int64_t strique_last_viterbi_declined(const strique_ctx *ctx) { return ctx ? ctx->last_viterbi_declined : 0; }
 extern "C" int strique_set_viterbi_exact(strique_ctx *ctx, int exact) {
     if (!ctx) return STRIQUE_EINVAL;
     ctx->viterbi_exact = exact != 0;
-    if (ctx->helper) ctx->helper->viterbi_exact = exact != 0;
     return STRIQUE_OK;
 }
 extern "C" float strique_last_stage_ms(const strique_ctx *ctx, int stage) {
@@ -140,86 +139,9 @@ extern "C" int strique_target_create(strique_ctx *ctx, const strique_target_desc
     return STRIQUE_OK;
 }
 
-static int detect_batch_serial(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
-                               int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
-                               strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap);
-
-// Optional (STRIQUE_PIPELINE_MIN): host-resident batches run as TWO half-batches in flight: the second half goes through a helper context (own
-// stream, own scratch, same models / targets) on a second host thread.  Every stage of one half that needs the
-// host (gating between alignment and HMM, task lists, result copies) and its upload over PCIe then overlap with
-// kernels of the other half, and the tail of one half's Viterbi launch is filled by the other half's kernels.
-// Device-resident batches (the bench's kernel-timing pass) stay serial so that the stage timers measure kernels.
-static int detect_batch_two_in_flight(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
-                                      int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
-                                      strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap) {
-    if (!ctx->helper) {
-        strique_ctx *h = new strique_ctx();
-        h->device = ctx->device;
-        h->num_sms = ctx->num_sms;
-        h->is_helper = true;
-        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-        cudaError_t e;
-        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
-            delete h;
-            FAIL(ctx, STRIQUE_ECUDA, std::string("helper stream/event creation: ") + cudaGetErrorString(e));
-        }
-        ctx->helper = h;
-    }
-    strique_ctx *h = ctx->helper;
-    h->models = ctx->models;          // shared, read only while a batch is in flight
-    h->targets = ctx->targets;
-    const int64_t total = raw_offsets[n_reads];
-    int r_mid = 1;
-    while (r_mid < n_reads - 1 && raw_offsets[r_mid] < total / 2) ++r_mid;
-    const int n1 = r_mid, n2 = n_reads - r_mid;
-    const size_t esz = raw_kind == 0 ? 2 : 8;
-    const int64_t base = raw_offsets[r_mid];
-    std::vector<int64_t> off2(n2 + 1);
-    for (int r = 0; r <= n2; ++r) off2[r] = raw_offsets[r_mid + r] - base;
-    int64_t cap1 = mod_out ? (int64_t)((double)mod_cap * ((double)base / (double)std::max<int64_t>(total, 1))) : 0;
-    cap1 = std::min(cap1, mod_cap);
-    const int64_t launches0 = h->launches;
-    int rc2 = STRIQUE_OK;
-    std::thread second([&]() {
-        rc2 = detect_batch_serial(h, cfg, n2, (const char *)raw + (size_t)base * esz, raw_kind, off2.data(), read_target + r_mid,
-                                  memspace, results + r_mid, mod_out ? mod_out + cap1 : nullptr, mod_out ? mod_cap - cap1 : 0);
-    });
-    const int rc1 = detect_batch_serial(ctx, cfg, n1, raw, raw_kind, raw_offsets, read_target, memspace, results, mod_out, cap1);
-    second.join();
-    if (rc1 != STRIQUE_OK) return rc1;
-    if (rc2 != STRIQUE_OK) { ctx->error = h->error; return rc2; }
-    for (int r = r_mid; r < n_reads; ++r)
-        if (results[r].mod_len >= 0) results[r].mod_off += cap1;
-    ctx->launches += h->launches - launches0;
-    ctx->last_align_cells += h->last_align_cells;
-    ctx->last_viterbi_edges += h->last_viterbi_edges;
-    for (int i = 0; i < 8; ++i) ctx->stage_ms[i] += h->stage_ms[i];   // the halves overlap: sums, not wall time
-    return STRIQUE_OK;
-}
-
 extern "C" int strique_detect_batch(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
                                     int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
                                     strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap) {
-    if (!ctx) return STRIQUE_EINVAL;
-    if (!cfg || n_reads < 0 || (raw_kind != 0 && raw_kind != 1) || cfg->samples <= 0)
-        FAIL(ctx, STRIQUE_EINVAL, "strique_detect_batch: bad argument");
-    if (n_reads == 0) return STRIQUE_OK;
-    if (!raw || !raw_offsets || !read_target || !results) FAIL(ctx, STRIQUE_EINVAL, "strique_detect_batch: null pointer");
-    // STRIQUE_PIPELINE_MIN: smallest host-resident batch that is split in two halves in flight.  Off unless set:
-    // measured on C2 (8192 reads) the two halves' kernels mostly run side by side instead of staggered, 264 ... 369
-    // ms per step against 268 ms serial -- it needs a deliberate stagger to pay off.
-    const char *pm = getenv("STRIQUE_PIPELINE_MIN");
-    const int pipe_min = pm ? atoi(pm) : 0;
-    if (memspace != STRIQUE_DEVICE && !ctx->is_helper && pipe_min > 0 && n_reads >= std::max(pipe_min, 2))
-        return detect_batch_two_in_flight(ctx, cfg, n_reads, raw, raw_kind, raw_offsets, read_target, memspace, results,
-                                          mod_out, mod_cap);
-    return detect_batch_serial(ctx, cfg, n_reads, raw, raw_kind, raw_offsets, read_target, memspace, results, mod_out, mod_cap);
-}
-
-static int detect_batch_serial(strique_ctx *ctx, const strique_detect_config *cfg, int n_reads, const void *raw,
-                               int raw_kind, const int64_t *raw_offsets, const int32_t *read_target, int memspace,
-                               strique_detect_result *results, uint8_t *mod_out, int64_t mod_cap) {
     if (!ctx) return STRIQUE_EINVAL;
     if (!cfg || n_reads < 0 || (raw_kind != 0 && raw_kind != 1) || cfg->samples <= 0)
         FAIL(ctx, STRIQUE_EINVAL, "strique_detect_batch: bad argument");
@@ -231,6 +153,7 @@ static int detect_batch_serial(strique_ctx *ctx, const strique_detect_config *cf
     stage_reset(ctx);
     ctx->last_viterbi_edges = 0;
     ctx->last_viterbi_fixed = ctx->last_viterbi_declined = 0;
+    ctx->last_mod_bytes = 0;
     const bool use_mod = cfg->use_mod != 0;
     // ---- 1. conditioning ------------------------------------------------------------------------
     const void *raw_dev = nullptr;
@@ -386,7 +309,9 @@ static int detect_batch_serial(strique_ctx *ctx, const strique_detect_config *cf
             dst_off[i] = mod_used;
             mod_used += plen[i];
         }
-        if (mod_used > mod_cap || (mod_used > 0 && !mod_out)) FAIL(ctx, STRIQUE_EINVAL, "mod_out buffer too small");
+        ctx->last_mod_bytes = mod_used;
+        // the caller retries with a buffer of strique_last_mod_bytes() bytes
+        if (mod_used > mod_cap || (mod_used > 0 && !mod_out)) FAIL(ctx, STRIQUE_ENOSPC, "mod_out buffer too small");
         if (mod_used > 0) {
             DevBuf &d_se = ctx->buf("pl.pat_srcend"), &d_do = ctx->buf("pl.pat_dstoff"), &d_pl = ctx->buf("pl.pat_len"),
                    &d_out = ctx->buf("pl.pat_out");

@@ -42,23 +42,6 @@ struct VitModelDev {
     const int32_t *perm;           // device position -> caller's emitting state id
 };
 
-// Device view of a model packed for the team kernel (viterbi_fast.cu): WPS warps per sequence, per
-// warp NH slots of <= 6 in-edges, NL slots of <= 3 in-edges and QC chain states per lane.  Value
-// column positions: emitting (w * (NH+NL) + slot) * 32 + lane, chain CB + (w * 32 + lane) * QC + q,
-// then START, then NEG.  All blob arrays are lane-minor ([...][32]).
-struct VitFastModelDev {
-    const unsigned char *blob;
-    int blob_bytes;
-    int off_w, off_src, off_em, off_flags, off_predw, off_cw, off_wr, off_csrc, off_end_w, off_end_src;
-    int n_end, C;
-    const int32_t *perm;           // value position -> caller's emitting state id
-};
-
-struct VitFastShape {              // which instantiation of the team kernel serves the model (wps == 0: none)
-    int wps = 0, nh = 0, nl = 0, qc = 0;
-    bool operator==(const VitFastShape &o) const { return wps == o.wps && nh == o.nh && nl == o.nl && qc == o.qc; }
-};
-
 // Device view of a model packed for the profile kernel (viterbi_profile.cu, profile_pack.h): the per-lane
 // constant table, per (position, slot) emission / flag tables for the slow emission path and the
 // traceback, the long-range (repeat loop) sources and the END edges.
@@ -88,33 +71,13 @@ struct VitProfModelDev {
 struct HmmModel {                 // host-side handle; device arrays owned by the context
     VitModelDev dev;
     int64_t n_edges = 0;          // in-edges of emitting + chain states (work unit of the Viterbi stage)
-    VitFastShape shape;
-    VitFastModelDev fast;
     bool has_profile = false;
     VitProfModelDev profile;
 };
 
-struct VitCtaTask {                // <= 8/WPS sequences of one model, consecutive in `order`
+struct VitCtaTask {                // a few sequences of one model, consecutive in `order`
     int32_t model, first, count;
 };
-
-struct VitFastBatch {
-    const double *x;
-    const int64_t *x_off;
-    const int32_t *order;
-    const VitCtaTask *tasks;
-    int n_tasks;
-    const VitFastModelDev *models; // device array indexed by VitCtaTask::model
-    int blob_cap;                  // shared-memory bytes reserved for the model blob (multiple of 16)
-    uint32_t *bp;
-    const int64_t *bp_off;         // [n_seq] offset in 32-bit words (per sequence: (T+1) * WPS * 32 words)
-    VitResult *res;
-    uint8_t *pattern;
-    uint16_t *path;
-    int *queue;
-};
-
-
 
 struct VitProfBatch {
     const double *x;
@@ -150,10 +113,6 @@ int viterbi_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
 // small-model kernel (viterbi_small.cu): <= 32 emitting states, no chain, <= 8 in-edges per state
 bool viterbi_small_fits(const VitModelDev &m);
 int viterbi_small_launch(strique_ctx *ctx, const HmmModel &m, const VitBatch &b);
-// team kernel: packs the model if one of the instantiated shapes fits (sets m->shape), launch
-int viterbi_fast_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
-int viterbi_fast_launch(strique_ctx *ctx, const VitFastShape &shape, const VitFastBatch &b);
-int viterbi_fast_teams(const VitFastShape &shape);   // sequences per CTA task
 // profile kernel: packs the model if its layout hints describe a linear profile (sets m->has_profile), launch
 int viterbi_profile_pack(strique_ctx *ctx, const strique_hmm_desc *d, HmmModel *m);
 int viterbi_profile_max_grid(strique_ctx *ctx, int *warps_per_cta);

@@ -91,14 +91,15 @@ def simulate_read(tab, bases, rng, scale=8.0, shift=100.0):
 
 
 def make_reads(pm, n_reads, seed=0, loci=('c9orf72',), n_lo=2, n_hi=1000, flank=1000, pm_mod=None, mod_fraction=0.0,
-               fixed_n=None):
+               fixed_n=None, indices=None):
     """-> list of (target_name, int16 signal, strand, true repeat count).  Reads are independent:
-    read r uses numpy default_rng([seed, r]) so any subset can be regenerated on its own."""
+    read r uses numpy default_rng([seed, r]) so any subset can be regenerated on its own (`indices`: the reads to
+    make, default range(n_reads))."""
     tab = KmerTable(pm)
     tab_mod = KmerTable(pm_mod) if pm_mod is not None else None
     enc = {name: tuple(encode(s) for s in LOCI[name]) for name in loci}
     out = []
-    for r in range(n_reads):
+    for r in (range(n_reads) if indices is None else indices):
         rng = np.random.default_rng([seed, r])
         name = loci[int(rng.integers(len(loci)))]
         rep, pre, suf = enc[name]
@@ -111,3 +112,33 @@ def make_reads(pm, n_reads, seed=0, loci=('c9orf72',), n_lo=2, n_hi=1000, flank=
         t = tab_mod if (tab_mod is not None and rng.random() < mod_fraction) else tab
         out.append((name, simulate_read(t, bases, rng), strand, n))
     return out
+
+
+# ---- the same reads, generated by a pool of processes (the bench's workload: seconds instead of tens of seconds) ----
+_pool_args = None
+
+
+def _pool_init(model_file, mod_model_file, kwargs):
+    global _pool_args
+    from .pore_model import pore_model
+    _pool_args = (pore_model(model_file), pore_model(mod_model_file) if mod_model_file else None, kwargs)
+
+
+def _pool_chunk(indices):
+    pm, pm_mod, kwargs = _pool_args
+    return make_reads(pm, 0, pm_mod=pm_mod, indices=indices, **kwargs)
+
+
+def make_reads_parallel(model_file, mod_model_file, indices, procs=None, chunk=64, **kwargs):
+    """make_reads(indices=...) over `procs` worker processes; the result is identical, read for read."""
+    import multiprocessing as mp
+    import os
+    indices = list(indices)
+    procs = max(1, min(procs or (os.cpu_count() or 1), (len(indices) + chunk - 1) // chunk))
+    if procs == 1:
+        _pool_init(model_file, mod_model_file, kwargs)
+        return _pool_chunk(indices)
+    chunks = [indices[i:i + chunk] for i in range(0, len(indices), chunk)]
+    with mp.get_context('fork').Pool(procs, initializer=_pool_init, initargs=(model_file, mod_model_file, kwargs)) as pool:
+        parts = pool.map(_pool_chunk, chunks, chunksize=1)
+    return [r for part in parts for r in part]

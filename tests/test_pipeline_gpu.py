@@ -87,26 +87,3 @@ def test_bundled_c9orf72_read(ctx, model_file):
     assert got[1] == 6.358286602121677 and got[2] == 6.086084196539416
     assert got[3] == pytest.approx(-121549.34988420883, rel=1e-9)
     assert got[6] == '-'
-
-
-def test_two_half_batches_in_flight_equal_the_serial_path(ctx, model_file, mod_model_file, monkeypatch):
-    """Host-resident batches of >= STRIQUE_PIPELINE_MIN reads are split into two halves decoded concurrently
-    (second host thread + helper context, csrc/pipeline.cu); results, including the methylation patterns that the
-    halves write into separate parts of the output buffer, must equal the serial path's."""
-    from strique_b200 import workload
-    dt = repeatCounter(model_file, mod_model_file=mod_model_file, context=ctx)
-    for name in ('c9orf72', 'fmr1'):
-        dt.add_target(name, *workload.LOCI[name])
-    reads = workload.make_reads(dt.pm, 11, seed=77, loci=('c9orf72', 'fmr1'), n_lo=2, n_hi=120, pm_mod=dt.pm_mod,
-                                mod_fraction=0.5)
-    items = [(name, sig, strand) for name, sig, strand, _ in reads]
-    monkeypatch.setenv('STRIQUE_PIPELINE_MIN', '0')
-    serial = dt.detect_batch(items)
-    monkeypatch.setenv('STRIQUE_PIPELINE_MIN', '2')
-    launches0 = ctx.launches
-    piped = dt.detect_batch(items)
-    assert ctx.launches > launches0
-    assert piped == serial
-    assert any(len(r[6]) > 3 for r in serial)        # the methylation stage ran
-    piped_again = dt.detect_batch(items[:3])         # odd split, helper context reused
-    assert piped_again == serial[:3]
