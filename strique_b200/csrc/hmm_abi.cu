@@ -289,12 +289,16 @@ int viterbi_run_device_multi(strique_ctx *ctx, const int32_t *seq_model, const d
                     tmp.resize(n_seq);
                     CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), d_res.p, (size_t)n_seq * sizeof(VitResult), cudaMemcpyDeviceToHost, ctx->stream));
                     { HostTimer ht("vit fixed-point kernel sync"); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); }
-                    size_t declined = 0;
-                    for (int32_t s : fixed_ids)
-                        if (tmp[s].status == 3) { exact_ids.push_back(s); ++declined; }
-                    ctx->last_viterbi_fixed += (int64_t)(fixed_ids.size() - declined);
-                    ctx->last_viterbi_declined += (int64_t)declined;
-                    if (declined) std::stable_sort(exact_ids.begin(), exact_ids.end(), [&](int a, int b) { return len(a) > len(b); });
+                    // sequences the fixed-point pass could not vouch for were decoded in float64 inside the same launch
+                    // (reserved = 1); status 3 would be a sequence left undecided -- the float64 kernel takes it
+                    size_t declined = 0, undecided = 0;
+                    for (int32_t s : fixed_ids) {
+                        if (tmp[s].status == 3) { exact_ids.push_back(s); ++undecided; }
+                        else if (tmp[s].reserved == 1) ++declined;
+                    }
+                    ctx->last_viterbi_fixed += (int64_t)(fixed_ids.size() - declined - undecided);
+                    ctx->last_viterbi_declined += (int64_t)(declined + undecided);
+                    if (undecided) std::stable_sort(exact_ids.begin(), exact_ids.end(), [&](int a, int b) { return len(a) > len(b); });
                 }
                 if (!exact_ids.empty()) {
                     TRY(run_pass(exact_ids, false));

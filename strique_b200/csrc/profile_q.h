@@ -4,21 +4,32 @@
 // 4l..4l+3; replaces pomegranate 0.10.0 `HiddenMarkovModel.viterbi` for the linear profile topologies of the
 // reference, scripts/STRique.py:201-441), but the forward pass runs on TAGGED 32-bit FIXED-POINT scores:
 //
-//   * a score is an int32 in units of 2^-19 nat relative to a running column maximum; its low 3 bits are zero
-//     ("clean"), so the resolution of a value is 2^-16 nat (fp32 at |log p| ~ 1e4 resolves 1e-3);
+//   * a score is an int32 in units of 2^-18 nat relative to a running column maximum; its low 3 bits are zero
+//     ("clean"), so the resolution of a value is 2^-15 nat = 3e-5 (fp32 at |log p| ~ 1e4 resolves 1e-3) and the
+//     range 8192 nat;
 //   * every in-edge weight carries the NAME of its edge in its low 3 bits ("tag", larger = earlier in the
 //     reference's candidate order).  One `max(v + w, best)` -- a single VIADDMNMX on sm_100a -- therefore relaxes
 //     the edge AND keeps the winner's name: the arg-max costs no instruction, and the first candidate wins exact
 //     ties like the strict '>' of the float64 decoder;
 //   * integer sums do not round: a path's fixed-point score differs from its float64 score only by the rounding
-//     of the weights (once per model) and of the emissions (2^-17 each), never by the order of operations;
-//   * every R_NORM columns the column maximum is subtracted (renormalisation) and values more than |Q_KILL| nat
-//     below it are declared unreachable (Q_NEG).  The constants below make int32 overflow impossible.
+//     of the weights (once per model) and of the emissions (2^-16 each), never by the order of operations;
+//   * every R_NORM columns the column maximum is subtracted (renormalisation) and values are clamped FROM BELOW at
+//     Q_FLOOR (unreachable states start there too).  Clamping only ever RAISES a value, and max-plus is monotone, so
+//     every forward value is an upper bound of the state's true fixed-point score, exact wherever no clamped value
+//     won on the way.  The traceback therefore re-adds the quantised weights and emissions along the decoded path in
+//     integers: if the sum equals the forward value, no clamp (floor or emission clamp) touched the winning path,
+//     and because every other path's forward value bounds its score from above, the decoded path is EXACTLY the
+//     optimum of the quantised model.  If not -- a read whose best path dips more than |Q_FLOOR| nat below the column
+//     maximum -- the sequence is decoded in float64.  (Reads whose flank alignment went wrong make the best path run
+//     700 ... 900 nat below the column maximum for ~2000 columns, 4 of 8192 C2 reads, and "teleporting" paths out of
+//     clamped states then need the floor well below that: hence 2^-15 nat with the floor at -2000 rather than 2^-16
+//     with -1024, which costs 1 more near-tie path difference in 512 golden reads and no integer output.)  (The first version declared such
+//     states unreachable instead; that is not conservative, and those 4 reads came back with a worse path.)
+//     The constants below make int32 overflow impossible.
 //
-// log p is NOT taken from the fixed-point pass: the traceback re-scores the decoded path in float64 with the
-// model's original weights and emissions, so log p is the exact score of the returned path.  The forward value and
-// the re-scored value must agree within the quantisation bound, otherwise (and for samples outside the fast
-// emission range, unreachable ends, models outside the bounds) the sequence is handed to the float64 kernel.
+// log p is NOT taken from the fixed-point pass: the traceback also re-scores the decoded path in float64 with the
+// model's original weights and emissions, so log p is the exact float64 score of the returned path.  Samples
+// outside the fast emission range, models outside the bounds and paths that touch a clamp go to the float64 kernel.
 //
 // Back-pointer byte of position q of a lane (4 per 32-bit word, one word per lane per column):
 //     bits 0-2  M: 7 self, 6 M_{p-1}, 5 I_{p-1}, 4 I_p, 3 M_{p-2}, 2 X_M, 1 D_{p-1}
@@ -34,22 +45,33 @@ namespace strique {
 namespace pq {
 
 constexpr int P = pf::P;
-constexpr int FRAC = 16;                         // value resolution 2^-16 nat
+#ifndef PQ_FRAC
+#define PQ_FRAC 15
+#endif
+constexpr int FRAC = PQ_FRAC;                    // value resolution 2^-FRAC nat
 constexpr int TAG_BITS = 3;
 constexpr int32_t TAG_MASK = 7;
 constexpr int32_t Q_ONE = 1 << (FRAC + TAG_BITS);   // one nat
-constexpr int R_NORM = 4;                        // columns between renormalisations
+#ifndef PQ_RNORM
+#define PQ_RNORM 4
+#endif
+constexpr int R_NORM = PQ_RNORM;                 // columns between renormalisations
 // bounds in nat (see the overflow argument in DESIGN.md 4.3): finite weights >= -W_MAX, emissions clamped to
 // >= -E_MAX, emission constants <= C0_MAX, so a value drops by at most S = W_MAX + E_MAX per column.
 constexpr int W_MAX = 12, E_MAX = 100, C0_MAX = 2, S_STEP = W_MAX + E_MAX;
-constexpr int Q_KILL_NAT = -640;                 // below this (relative to the column maximum): unreachable
-constexpr int Q_ABSENT_NAT = -1152;              // weight of an edge the model does not have
-constexpr int Q_NEG_NAT = -1152;                 // value of an unreachable state after a renormalisation
-static_assert(-Q_ABSENT_NAT >= -Q_KILL_NAT + R_NORM * S_STEP + W_MAX + R_NORM * C0_MAX, "an absent edge must lose against every live candidate");
-static_assert(Q_KILL_NAT - Q_NEG_NAT > R_NORM * S_STEP, "an unreachable state must not drift back above the kill line");
-static_assert(-Q_NEG_NAT + R_NORM * S_STEP + 2 * -Q_ABSENT_NAT + W_MAX < 4096, "int32 range (4096 nat at 2^-19)");
-constexpr int32_t Q_KILL = Q_KILL_NAT * Q_ONE, Q_ABSENT = Q_ABSENT_NAT * Q_ONE, Q_NEG = Q_NEG_NAT * Q_ONE;
-constexpr int32_t E_MIN16 = -E_MAX * (1 << FRAC);   // emission clamp in units of 2^-16
+#ifndef PQ_FLOOR
+#define PQ_FLOOR 2000
+#define PQ_ABSENT 2500
+#endif
+constexpr int Q_FLOOR_NAT = -PQ_FLOOR;           // values are clamped from below here (relative to the column maximum)
+constexpr int Q_ABSENT_NAT = -PQ_ABSENT;         // weight of an edge the model does not have
+// a candidate through an absent edge (best source: the column maximum, grown for R_NORM columns) stays below every
+// candidate through a real edge (worst source: the floor, decayed for R_NORM columns) -- it can never win
+static_assert(-Q_ABSENT_NAT >= -Q_FLOOR_NAT + R_NORM * S_STEP + W_MAX + R_NORM * C0_MAX, "an absent edge must lose against every real candidate");
+// lowest intermediate: floor, decayed, through an absent entry and an absent hop of the delete chain
+static_assert(-Q_FLOOR_NAT + R_NORM * S_STEP + 2 * -Q_ABSENT_NAT + W_MAX < (1 << (31 - FRAC - TAG_BITS)), "int32 range");
+constexpr int32_t Q_FLOOR = Q_FLOOR_NAT * Q_ONE, Q_ABSENT = Q_ABSENT_NAT * Q_ONE;
+constexpr int32_t E_MIN16 = -E_MAX * (1 << FRAC);   // emission clamp in units of 2^-FRAC
 
 // Per-lane table of a quantised model: int32 groups of four (fetched as one 16-byte word) ...
 enum : int {
@@ -93,9 +115,9 @@ struct StateQ {
     int32_t Dprev;                  // D of the last position of the previous lane (same column as D[], clean)
 };
 
-// magic-number rounding of a float64 emission to units of 2^-16 (round to nearest even, exact for |e| < 32768)
+// magic-number rounding of a float64 emission to units of 2^-FRAC (round to nearest even, exact for |e| < 2^(31 - FRAC))
 PF_HD int32_t to_q16(double e) {
-    const double t = e + 103079215104.0;         // 1.5 * 2^36: ulp 2^-16 in [2^36, 2^37)
+    const double t = e + 1.5 * (double)(1ull << (52 - FRAC));   // FRAC = 16: 1.5 * 2^36, ulp 2^-16 in [2^36, 2^37)
 #ifdef __CUDA_ARCH__
     return __double2loint(t);
 #else
@@ -113,12 +135,16 @@ PF_HD double fma_rn(double a, double b, double c) {
 #endif
 }
 
+// Emission from the constants {A, c, C} of a state (see E_MU), x2 = x * x: units of 2^-16, clamped at E_MIN16.
+PF_HD int32_t emission_q16(double A, double c, double C, double x, double x2) {
+    return imax(to_q16(fma_rn(-c, x2, fma_rn(A, x, C))), E_MIN16);
+}
 // Emission of the M slot of in-lane position q for sample x (inside every Uniform range, not NaN), x2 = x * x:
 // units of 2^-16, clamped.  Two fused multiply-adds and the rounding add.
 template <class Tab>
 PF_HD int32_t emission_q(const Tab &tab, double x, double x2, int q) {
     const pf::Pair em = tab.dpair(E_MU + q), cc = tab.dpair(E_C0 + q / 2);
-    return imax(to_q16(fma_rn(-em.b, x2, fma_rn(em.a, x, (q & 1) ? cc.b : cc.a))), E_MIN16);
+    return emission_q16(em.a, em.b, (q & 1) ? cc.b : cc.a, x, x2);
 }
 template <class Tab>
 PF_HD void emissions_q(const Tab &tab, double x, int32_t eM[P]) {
@@ -232,13 +258,12 @@ PF_HD int32_t lane_max(const StateQ &s) {
     for (int q = 1; q < P; ++q) m = imax(imax(s.M[q], s.I[q]), m);
     return m;
 }
-// ... and the shift by the column maximum mx; values that fall below the kill line become unreachable.
+// ... and the shift by the column maximum mx, clamped from below at the floor (one add-max per value).
 PF_HD void renorm(StateQ &s, int32_t mx) {
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const int32_t m = s.M[q] - mx, i = s.I[q] - mx;
-        s.M[q] = m < Q_KILL ? Q_NEG : m;
-        s.I[q] = i < Q_KILL ? Q_NEG : i;
+        s.M[q] = imax(s.M[q] - mx, Q_FLOOR);
+        s.I[q] = imax(s.I[q] - mx, Q_FLOOR);
     }
 }
 

@@ -61,11 +61,15 @@ struct VitProfModelDev {
     // float64 kernel
     const int32_t *qgrp;           // [pq::G_TOTAL][32][4]
     const double *qem;             // [pq::E_TOTAL][32][2]
-    // its traceback re-scores the path in float64: one record per (position, slot in {M, I}), index position * 2 +
-    // slot: {a, b, c, self-loop weight} with emission = b - (x - a)^2 c (Uniform / unused slot: a = 0, c = 0), and
-    // flags | caller's state id << 16
-    const double *trec;            // [pf::NPOS * 2][4]
+    // its traceback re-scores the path in float64 and re-adds it in fixed point: one record per (position, slot in
+    // {M, I}), index position * 2 + slot: {a, b, c, self-loop weight} with emission = b - (x - a)^2 c (Uniform / unused
+    // slot: a = 0, c = 0), then the constants of the forward pass's own emission {A, c, C, 0} (profile_q.h);
+    // tmeta: flags | caller's state id << 16; tq: {quantised self-loop weight, quantised I-slot emission}; qtab: the
+    // quantised weights without their tags, indexed like `tab` (INT32_MIN: the model has no such edge)
+    const double *trec;            // [pf::NPOS * 2][8]
     const uint32_t *tmeta;         // [pf::NPOS * 2]
+    const int32_t *tq;             // [pf::NPOS * 2][2]
+    const int32_t *qtab;           // [pf::K_TOTAL][32]
 };
 
 struct HmmModel {                 // host-side handle; device arrays owned by the context

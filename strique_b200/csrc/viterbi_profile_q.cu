@@ -14,7 +14,7 @@
 #include <algorithm>
 
 #include "profile_q_pack.h"
-#include "viterbi.cuh"
+#include "viterbi_profile_dev.cuh"
 
 namespace strique {
 
@@ -30,7 +30,10 @@ constexpr int PROFQ_WARPS = PROFQ_WARPS_PER_CTA;
 constexpr int PROFQ_CTAS_PER_SM = PROFQ_CTAS;
 constexpr int PROFQ_STAGE_ROWS = 32;
 constexpr int PROFQ_BUF_BYTES = PROFQ_STAGE_ROWS * 32 * 4 + PROFQ_STAGE_ROWS * 8;   // 32 back-pointer rows + their samples
-constexpr int PROFQ_STAGE_BYTES = 2 * PROFQ_BUF_BYTES;            // per warp: two buffers (the traceback prefetches)
+// per warp: two buffers (the traceback prefetches), or -- while the warp decodes a sequence in float64 -- that
+// decoder's model table and its staging area
+constexpr int PROFQ_STAGE_BYTES = 2 * PROFQ_BUF_BYTES > f64::PROF_AUX_BYTES + f64::PROF_STAGE_BYTES
+                                      ? 2 * PROFQ_BUF_BYTES : f64::PROF_AUX_BYTES + f64::PROF_STAGE_BYTES;
 static_assert(PROFQ_STAGE_BYTES >= 3 * pf::NPOS * 4, "the END gather reuses the stage area");
 
 // This lane's constants of the warp's current model, ALL in registers (59 weights, 12 float64 emission constants):
@@ -138,17 +141,17 @@ __device__ __forceinline__ void renormalise(pq::StateQ &S, long long &off) {
 
 // Forward pass of one sequence.  Returns false when a sample lies outside the fast emission range (declined).
 // Columns 1..4 and the last T mod 4 go one at a time; in between, groups of four columns are unrolled with the
-// renormalisation at the end of the group (no branch), their samples fetched one group ahead: the tag packing, the
+// renormalisations in place (no branch), their samples fetched one group ahead: the tag packing, the
 // stores and the emissions of neighbouring columns then overlap with the shuffle latencies of the scan.
 template <int XQ>
 __device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms, const int lane,
                                         pq::StateQ &S, const SeqCtx &c, long long &off) {
 #pragma unroll
     for (int q = 0; q < pq::P; ++q) {
-        S.M[q] = (lane * pq::P + q == ms.p_start) ? 0 : pq::Q_NEG;    // START: value 0 before the first sample only
-        S.I[q] = S.D[q] = S.partM[q] = S.partI[q] = pq::Q_NEG;
+        S.M[q] = (lane * pq::P + q == ms.p_start) ? 0 : pq::Q_FLOOR;    // START: value 0 before the first sample only
+        S.I[q] = S.D[q] = S.partM[q] = S.partI[q] = pq::Q_FLOOR;
     }
-    S.Dprev = pq::Q_NEG;
+    S.Dprev = pq::Q_FLOOR;
     off = 0;
     // the trip count through a warp reduction: its result lives in a uniform register (see the kernel)
     const int T = __reduce_max_sync(FULL, c.T);
@@ -158,34 +161,38 @@ __device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms,
     uint32_t *bp = c.bp + lane;
     int t = 1;
 #pragma unroll 1
-    for (; t <= T && t <= pq::R_NORM; ++t) {
+    for (; t <= T && t <= 4; ++t) {
         column<XQ>(tab, ms, S, __ldg(x + t - 1), ok, word, bp);
         if (t == 1) {                                                 // START does not outlive the first column
 #pragma unroll
             for (int q = 0; q < pq::P; ++q)
-                if (lane * pq::P + q == ms.p_start) S.M[q] = pq::Q_NEG;
+                if (lane * pq::P + q == ms.p_start) S.M[q] = pq::Q_FLOOR;
             renormalise(S, off);
         }
-        if (t == pq::R_NORM) renormalise(S, off);
+        if ((t & (pq::R_NORM - 1)) == 0) renormalise(S, off);
     }
-    static_assert(pq::R_NORM == 4, "the group loop below is written for four columns");
+    static_assert(pq::R_NORM == 2 || pq::R_NORM == 4, "the group loop below renormalises after two or four columns");
     if (t + 3 <= T) {
         double x0 = __ldg(x + t - 1), x1 = __ldg(x + t), x2 = __ldg(x + t + 1), x3 = __ldg(x + t + 2);
 #pragma unroll 1
-        for (; t + 3 <= T; t += 4) {
+        for (; t + 3 <= T; t += 4) {                                  // t = 5, 9, ...: t + 3 is a multiple of four
             const bool more = t + 7 <= T;
             const double n0 = more ? __ldg(x + t + 3) : 0.0, n1 = more ? __ldg(x + t + 4) : 0.0,
                          n2 = more ? __ldg(x + t + 5) : 0.0, n3 = more ? __ldg(x + t + 6) : 0.0;
             column<XQ>(tab, ms, S, x0, ok, word, bp);
             column<XQ>(tab, ms, S, x1, ok, word, bp);
+            if (pq::R_NORM == 2) renormalise(S, off);
             column<XQ>(tab, ms, S, x2, ok, word, bp);
             column<XQ>(tab, ms, S, x3, ok, word, bp);
-            renormalise(S, off);                                      // t + 3 is a multiple of four
+            renormalise(S, off);
             x0 = n0; x1 = n1; x2 = n2; x3 = n3;
         }
     }
 #pragma unroll 1
-    for (; t <= T; ++t) column<XQ>(tab, ms, S, __ldg(x + t - 1), ok, word, bp);
+    for (; t <= T; ++t) {
+        column<XQ>(tab, ms, S, __ldg(x + t - 1), ok, word, bp);
+        if ((t & (pq::R_NORM - 1)) == 0) renormalise(S, off);
+    }
     int32_t unused[pq::P];
     *bp = word | block<XQ>(tab, ms, S, 0.0, unused);                  // column T: delete chain (END edges may leave it)
     return ok;
@@ -193,7 +200,7 @@ __device__ __forceinline__ bool forward(const TabQ &tab, const ModelScalars &ms,
 
 // END edges: best (v[T][src] + w), first maximum; unreachable sources do not count
 __device__ __forceinline__ void end_edges(const VitProfModelDev &m, const pq::StateQ &S, uint32_t *stage, const int lane,
-                                          double &best_out, int &barg_out) {
+                                          double &best_out, int &barg_out, int32_t &vend_out) {
     const double NINF = pf::ninf();
     __syncwarp();
     int32_t *vals = reinterpret_cast<int32_t *>(stage);
@@ -206,12 +213,11 @@ __device__ __forceinline__ void end_edges(const VitProfModelDev &m, const pq::St
     __syncwarp();
     double best = NINF;
     int barg = -1;
+    int32_t v = 0;
     if (lane < m.n_end) {
-        const int32_t v = vals[m.end_slot[lane] * pf::NPOS + m.end_p[lane]];
-        if (v >= pq::Q_KILL - pq::R_NORM * pq::S_STEP * pq::Q_ONE) {
-            best = (double)v * (1.0 / (double)pq::Q_ONE) + m.end_w[lane];
-            barg = lane;
-        }
+        v = vals[m.end_slot[lane] * pf::NPOS + m.end_p[lane]];
+        best = (double)v * (1.0 / (double)pq::Q_ONE) + m.end_w[lane];
+        barg = lane;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -221,13 +227,15 @@ __device__ __forceinline__ void end_edges(const VitProfModelDev &m, const pq::St
     }
     best_out = __shfl_sync(FULL, best, 0);
     barg_out = __shfl_sync(FULL, barg, 0);
+    vend_out = __shfl_sync(FULL, v, barg_out < 0 ? 0 : barg_out);
     __syncwarp();
 }
 
 // Traceback (all lanes walk in lock step; lane 0 / lane i write) with the float64 re-score of the path, and the
-// result record of one sequence.  vfwd = the forward pass's value of the path (relative part + END weight).
-__device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModelDev &m, const SeqCtx &c, uint32_t *stage,
-                                       const int lane, const int p_start, const double vfwd, const int barg) {
+// result record of one sequence.  vfwd_q = the forward pass's value of the END source state (fixed point, with the
+// subtracted column maxima added back): the path's quantised terms must add up to exactly this.
+__device__ __noinline__ bool traceback(const VitProfBatch &b, const VitProfModelDev &m, const SeqCtx &c, uint32_t *stage,
+                                       const int lane, const int p_start, const long long vfwd_q, const int barg) {
     const int T = c.T;
     const uint32_t *bp = c.bp;
     // the model's tables: pointers read once (the loop below stores through other pointers, so the compiler would
@@ -235,6 +243,10 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
     const double *__restrict__ tab = m.tab;
     const double2 *__restrict__ trec = reinterpret_cast<const double2 *>(m.trec);
     const uint32_t *__restrict__ tmeta = m.tmeta;
+    const int2 *__restrict__ tq = reinterpret_cast<const int2 *>(m.tq);
+    const int32_t *__restrict__ qtab = m.qtab;
+    long long qacc = 0;                   // this lane's share of the path's fixed-point score
+    bool clamped = false;                 // an emission at the clamp or an edge the model does not have
     const double *__restrict__ xs = c.x;
     VitResult r;
     r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 0; r.reserved = 0;
@@ -296,7 +308,12 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         if (slot == 2) {                  // silent delete state: same column
             int wk = 0;
             if (!pq::back_apply(c_back[pq::back_index(rows[(t - stage_lo) * 32 + tl], p, slot)], tc, p, slot, t, wk)) { r.status = 2; break; }
-            if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
+            if (lane == 0) {
+                acc += __ldg(tab + wk * 32 + tl);
+                const int32_t qw = __ldg(qtab + wk * 32 + tl);
+                clamped |= qw == INT32_MIN;
+                qacc += qw;
+            }
             continue;
         }
         if (t < 1) { r.status = 2; break; }
@@ -314,7 +331,9 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         const int visits = k + (step ? 1 : 0);                     // >= 1: column t itself is staged
         const int idx = p * 2 + slot;
         // everything that depends on the state only: loads issued together
-        const double2 ab = __ldg(trec + idx * 2), cw = __ldg(trec + idx * 2 + 1);
+        const double2 ab = __ldg(trec + idx * 4), cw = __ldg(trec + idx * 4 + 1), Ac = __ldg(trec + idx * 4 + 2),
+                      Cz = __ldg(trec + idx * 4 + 3);
+        const int2 qs = __ldg(tq + idx);
         const unsigned fl = __ldg(tmeta + idx);
         const int sid = (int)(fl >> 16);
         if (fl & HMM_FLAG_COUNT) r.n_count += visits;
@@ -329,35 +348,92 @@ __device__ __noinline__ void traceback(const VitProfBatch &b, const VitProfModel
         // re-score: lane i adds the emission of column t - i and, inside the run, the self-loop weight
         if (lane < visits) {
             // the forward pass has checked that every sample is a number inside all Uniform ranges
-            const double dx = xstage[ti - stage_lo] - ab.x;
+            const double x = xstage[ti - stage_lo];
+            const double dx = x - ab.x;
             acc += ab.y - (dx * dx) * cw.x;
-            if (lane < k) acc += cw.y;
+            // ... and the same terms as the forward pass added them
+            int32_t qe = qs.y;
+            if (slot == 0) {
+                const int32_t e16 = pq::emission_q16(Ac.x, Ac.y, Cz.x, x, x * x);
+                clamped |= e16 == pq::E_MIN16;
+                qe = e16 * 8;
+            }
+            qacc += qe;
+            if (lane < k) { acc += cw.y; qacc += qs.x; }
         }
         t -= k;
         if (step) {
             const uint32_t w = __shfl_sync(FULL, wfull, k);
             int wk = 0;
             if (!pq::back_apply(c_back[pq::back_index(w, p, slot)], tc, p, slot, t, wk)) { r.status = 2; break; }
-            if (lane == 0) acc += __ldg(tab + wk * 32 + tl);
+            if (lane == 0) {
+                acc += __ldg(tab + wk * 32 + tl);
+                const int32_t qw = __ldg(qtab + wk * 32 + tl);
+                clamped |= qw == INT32_MIN;
+                qacc += qw;
+            }
         }
     }
     if (in_group) { if (pat && lane == 0) pat[T - 1 - plen] = last_mod; ++plen; }
     if (r.status == 0 && t != 0) r.status = 2;
     r.pattern_len = plen;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    for (int off = 16; off > 0; off >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, off);
+        qacc += __shfl_xor_sync(FULL, qacc, off);
+    }
     r.logp = acc;
-    // the forward value of this path and its exact score differ by the rounding of <= 2 addends per column only
-    if (r.status == 0 && !(fabs(vfwd - acc) <= 1.0e-3 + (double)T * (2.0 / (double)(1 << pq::FRAC)))) r.status = 3;
-    if (r.status == 2) r.status = 3;      // let the float64 kernel have the last word
-    if (lane == 0) b.res[c.seq] = r;
+    // The forward value is an upper bound of the path's fixed-point score, exact unless a clamped value won on the
+    // way (profile_q.h): equality proves that the path is the optimum of the quantised model.
+    if (r.status == 0 && (qacc != vfwd_q || __any_sync(FULL, clamped))) r.status = 3;
+    // ... and its float64 score differs from that by the rounding of <= 2 addends per column only (sanity)
+    if (r.status == 0 && !(fabs((double)vfwd_q * (1.0 / (double)pq::Q_ONE) + m.end_w[barg] - acc) <=
+                           1.0e-3 + (double)T * (2.0 / (double)(1 << pq::FRAC)))) r.status = 3;
+    if (r.status == 2) r.status = 3;      // let the float64 decoder have the last word
+    if (r.status == 0 && lane == 0) b.res[c.seq] = r;
     __syncwarp();
+    return r.status == 0;
 }
 
-__device__ __forceinline__ void decline(const VitProfBatch &b, const SeqCtx &c, const int lane) {
-    VitResult r;
-    r.logp = 0.0; r.n_count = 0; r.t_first = -1; r.t_last = -1; r.pattern_len = 0; r.status = 3; r.reserved = 0;
-    if (lane == 0) b.res[c.seq] = r;
+// A sequence the fixed-point pass cannot vouch for: decoded again in float64, right here, by the same warp (the
+// float64 kernel's device code; the warp's staging area holds the model table meanwhile).  Such sequences are rare
+// (4 of 8192 C2 reads) and long; a second launch for them would be a serial tail of T x (latency of one column) --
+// 18 ms for 45 k samples -- while inside this launch it hides behind the other warps' sequences.  The result carries
+// status | 4 on the way out so that the host can count them.
+template <int XQ>
+__device__ __noinline__ void decode_float64(const VitProfBatch &b, const VitProfModelDev &m, const SeqCtx &c, uint32_t *stage,
+                                            const int lane) {
+    f64::ModelScalars fs;
+    fs.p_start = m.p_start;
+    const int xp = m.trace.xm_src_p >= 0 ? m.trace.xm_src_p : (m.trace.xd_src_p >= 0 ? m.trace.xd_src_p : 0);
+    fs.xlane = xp / pf::P; fs.xq = xp % pf::P;
+    fs.xm_slot = m.trace.xm_src_slot; fs.xd_slot = m.trace.xd_src_slot;
+    fs.lo = m.lo; fs.hi = m.hi;
+    pf::Regs R;
+    pf::load_regs(f64::TabGlobal{m.tab + lane}, R);
+    // the model's table: logical [k][lane] in global memory -> pair-interleaved in this warp's shared memory
+    __syncwarp();
+    double *aux_s = reinterpret_cast<double *>(stage);
+    for (int k = 0; k < pf::K_NAUX; ++k) aux_s[((k >> 1) * 32 + lane) * 2 + (k & 1)] = __ldg(m.tab + (pf::K_NREG + k) * 32 + lane);
+    __syncwarp();
+    const f64::AuxShared aux{reinterpret_cast<const double2 *>(aux_s) + lane};
+    stage += f64::PROF_AUX_BYTES / 4;
+    f64::SeqCtx fc[1];
+    fc[0].seq = c.seq; fc[0].T = c.T; fc[0].xo = c.xo; fc[0].x = c.x; fc[0].bp = c.bp;
+    pf::State S[1];
+    uint32_t bits[1];
+    f64::init_state(S[0], lane, fs.p_start);
+    double x0[1] = {c.T > 0 ? __ldg(c.x) : 0.0};
+    f64::block<1, XQ, f64::AuxShared>(R, aux, fs, S, bits);
+    c.bp[lane] = bits[0];
+    f64::forward<1, XQ, f64::AuxShared>(R, aux, fs, m, lane, S, fc, x0, 1, c.T);
+    double best;
+    int barg;
+    f64::end_edges(m, S[0], stage, lane, best, barg);
+    f64::traceback(b, m, fc[0], stage, lane, fs.p_start, best, barg);
+    __syncwarp();
+    if (lane == 0) b.res[c.seq].reserved = 1;             // decoded in float64
+    __syncwarp();
 }
 
 // one sequence, start to finish, by one warp
@@ -366,12 +442,15 @@ __device__ __forceinline__ void run_seq(const VitProfBatch &b, const VitProfMode
                                         const ModelScalars &ms, uint32_t *stage, const int lane) {
     pq::StateQ S;
     long long off;
-    if (!forward<XQ>(tab, ms, lane, S, c, off)) { decline(b, c, lane); return; }
-    double best;
-    int barg;
-    end_edges(m, S, stage, lane, best, barg);
-    if (barg < 0) { decline(b, c, lane); return; }
-    traceback(b, m, c, stage, lane, ms.p_start, best + (double)off * (1.0 / (double)pq::Q_ONE), barg);
+    bool ok = forward<XQ>(tab, ms, lane, S, c, off);
+    if (ok) {
+        double best;
+        int barg;
+        int32_t vend;
+        end_edges(m, S, stage, lane, best, barg, vend);
+        ok = barg >= 0 && traceback(b, m, c, stage, lane, ms.p_start, (long long)vend + off, barg);
+    }
+    if (!ok) decode_float64<XQ>(b, m, c, stage, lane);
 }
 
 // Persistent warps: every warp pulls whole sequences (longest first, all models of the batch in one queue) and
@@ -458,30 +537,24 @@ int viterbi_profile_q_pack(strique_ctx *ctx, const ProfileImage &img, VitProfMod
     f->qem = nullptr;
     f->trec = nullptr;
     f->tmeta = nullptr;
+    f->tq = nullptr;
+    f->qtab = nullptr;
     ProfileQImage qi;
     std::string why;
     if (!profile_quantise(img, &qi, &why)) return STRIQUE_OK;
-    std::vector<double> trec((size_t)pf::NPOS * 2 * 4, 0.0);
-    std::vector<uint32_t> tmeta((size_t)pf::NPOS * 2, 0u);
-    for (int p = 0; p < pf::NPOS; ++p)
-        for (int slot = 0; slot < 2; ++slot) {
-            const int idx = p * 2 + slot, q = p % pf::P, lane = p / pf::P;
-            const bool normal = img.em_kind[idx] == 0, uniform = img.em_kind[idx] == 1;
-            trec[idx * 4 + 0] = normal ? img.em_a[idx] : 0.0;
-            trec[idx * 4 + 1] = normal ? img.em_b[idx] : (uniform ? img.em_c[idx] : 0.0);
-            trec[idx * 4 + 2] = normal ? img.em_c[idx] : 0.0;
-            trec[idx * 4 + 3] = img.tab[(size_t)(slot == 0 ? pf::K_WMR + q * 4 : pf::K_WI + q * 2) * 32 + lane];
-            tmeta[idx] = (uint32_t)img.flags[idx] | ((uint32_t)(img.state_id[idx] & 0xffff) << 16);
-        }
-    void *pg = nullptr, *pe = nullptr, *pt = nullptr, *pm = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&pt, trec.size() * 8));
-    ctx->owned.push_back(pt);
-    CUDA_TRY(ctx, cudaMalloc(&pm, tmeta.size() * 4));
-    ctx->owned.push_back(pm);
-    CUDA_TRY(ctx, cudaMemcpy(pt, trec.data(), trec.size() * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(pm, tmeta.data(), tmeta.size() * 4, cudaMemcpyHostToDevice));
-    f->trec = (const double *)pt;
-    f->tmeta = (const uint32_t *)pm;
+    void *pg = nullptr, *pe = nullptr;
+    auto upload = [&](const void *src, size_t bytes, const void **dst) -> int {
+        void *p = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+        ctx->owned.push_back(p);
+        CUDA_TRY(ctx, cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        *dst = p;
+        return STRIQUE_OK;
+    };
+    TRY(upload(qi.trec.data(), qi.trec.size() * 8, (const void **)&f->trec));
+    TRY(upload(qi.tmeta.data(), qi.tmeta.size() * 4, (const void **)&f->tmeta));
+    TRY(upload(qi.tq.data(), qi.tq.size() * 4, (const void **)&f->tq));
+    TRY(upload(qi.qtab.data(), qi.qtab.size() * 4, (const void **)&f->qtab));
     CUDA_TRY(ctx, cudaMalloc(&pg, qi.grp.size() * 4));
     ctx->owned.push_back(pg);
     CUDA_TRY(ctx, cudaMalloc(&pe, qi.em.size() * 8));

@@ -168,7 +168,7 @@ def test_viterbi_kernels_agree(ctx, model_file, mod_model_file, monkeypatch):
         if has_profile:
             variants.append(('fixed', run()))
             n_fixed, n_declined = ctx.last_viterbi_fixed
-            assert n_fixed >= 8 and n_declined >= 5        # NaN / out-of-range sequences went to float64
+            assert n_fixed >= 5 and n_declined >= 5        # NaN / out-of-range / truncated sequences went to float64
         for name, (r1, p1, path1) in variants:
             fixed = name == 'fixed'
             assert np.array_equal(r1['status'], r0['status'])
