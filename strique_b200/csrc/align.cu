@@ -375,6 +375,189 @@ struct LinSweep {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// LinSweep2: the linear-gap scan with PACKED adds and a low register footprint (S even).
+//
+// Same recurrence as LinSweep, bit for bit (add.rn.f32x2 is two independent IEEE fp32 adds).  Of the three adds of a
+// cell, inter = S[j-1][i-1] + score and h = S[j-1][i] + g_h only read the previous column, so two rows share one
+// instruction each; v = S[j][i-1] + g_v is the serial chain down the column and stays scalar: 2 packed + 2 scalar
+// adds + 2 three-input maxima per TWO cells instead of 6 + 2.
+// For both packed adds to take the SAME aligned register pair (S[2m], S[2m+1]) of the previous column, the inter
+// pair must be the rows (2m+1, 2m+2) -- and for a pair never to straddle two flank levels (different scores) the
+// lane's strip starts one row early: lane l owns the DP rows i = l R + r, r = 0..R-1, i.e. its local row 0 is the
+// last row of the previous lane's last level (its score comes from that lane's table entry) and local rows
+// 1..R-1 are whole levels; lane 0's local row 0 is DP row 0 (free begin: S = 0, forced).  Checkpoints are stored
+// by DP row, so the trace pass is unaffected.
+// Measured (C2, 8192 reads): 97.4 ms against 99.5 ms for LinSweep at 16 single-warp CTAs per SM -- far less than the
+// column body alone promises (tools/micro/cell.cu, profiles/cell_r02.txt: 173 against 199 cycles per column and
+// scheduler at 16 warps per SM, 141 at 28), and MORE resident warps make the real kernel slower (18: 102 ms, 24:
+// 102 ms with spills, 28: 107 ms): every task streams its own 164 KB score table through L1, and beyond 16 tables
+// per SM the hit rate collapses.  What bounds the scan is the serial add -> max chain down every column, issued in
+// order (ncu scan2_r02: 39 % of the stall samples are fixed-latency waits on that chain, issue slots 72 % busy).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+template <int K, int S>
+struct LinSweep2 {
+    static constexpr int R = K * S;
+    static_assert(S % 2 == 0, "packed pairs must not straddle flank levels");
+
+    // sc[k], k < K: score of this lane's level k for the column's code; sc[K]: of the previous lane's last level
+    // scalar form: DP column 1 (FIRST: H of column 0 is SeqAn's "infinity") and the ragged first / last steps
+    template <bool FIRST>
+    __device__ __forceinline__ static float column(float (&Sv)[R], const float (&sc)[K + 1], float diag, float cS,
+                                                   const float gh, const float gv, const bool lane0) {
+        const float INF = STRIQUE_SEQAN_INF;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float pS = Sv[r];
+            const float inter = diag + (r == 0 ? sc[K] : sc[(r - 1) / S]);
+            diag = pS;
+            const float h = (FIRST ? fmaxf(INF, pS) : pS) + gh;
+            cS = fmax3(inter, h, cS + gv);
+            if (r == 0) cS = lane0 ? 0.f : cS;               // DP row 0: free begin
+            Sv[r] = cS;
+        }
+        return cS;
+    }
+
+    __device__ __forceinline__ static float column2(float (&Sv)[R], const float (&sc)[K + 1], const float diag, float cS,
+                                                    const unsigned long long gh2, const float gv, const bool lane0) {
+        float inter = diag + sc[K];
+#pragma unroll
+        for (int m = 0; m < R / 2; ++m) {
+            const unsigned long long P = f2_pack(Sv[2 * m], Sv[2 * m + 1]);
+            const float sck = sc[m / (S / 2)];               // rows 2m+1 and 2m+2 lie in the same level
+            float h0, h1, i1, i2;
+            f2_unpack(f2_add(P, gh2), h0, h1);
+            f2_unpack(f2_add(P, f2_pack(sck, sck)), i1, i2);
+            cS = fmax3(inter, h0, cS + gv);
+            if (m == 0) cS = lane0 ? 0.f : cS;
+            Sv[2 * m] = cS;
+            cS = fmax3(i1, h1, cS + gv);
+            Sv[2 * m + 1] = cS;
+            inter = i2;
+        }
+        return cS;
+    }
+
+    // rlk: the last DP row L is local row rlk * S of the last lane (L is a multiple of S).  RL0: rlk == 0 (the
+    // reference's 870-sample flanks: 870 = 29 * 30), the last row is the lane's first register -- no select chain
+    template <bool RL0>
+    __device__ __forceinline__ static void run(const uint16_t *__restrict__ codes, const int N,
+                                               const float *__restrict__ lut, const int lane, const int nl,
+                                               const strique_align_params &p, float (&Sv)[R], float diag_next,
+                                               const int rlk, float &best, int &bestj, float *__restrict__ ckS,
+                                               float *__restrict__ ckH, const int ckpt_rows, const int L) {
+        const float gh = p.gap_extension_h, gv = p.gap_extension_v;
+        const unsigned long long gh2 = f2_pack(gh, gh);
+        const int row_len = 32 * K;
+        const bool lane0 = lane == 0;
+        float lutc[K + 1], lutn[K + 1];
+        float botS = 0.f;
+        const int last_step = N + nl - 1;
+        const float *lut_lane = lut + lane;                       // code row stored [k][lane]
+        const int prev_off = (K - 1) * 32 - (lane0 ? 0 : 1);     // previous lane's last level (lane 0: unused)
+        auto fetch = [&](const int code, float (&dst)[K + 1]) {
+            const float *row = lut_lane + (size_t)code * row_len;
+#pragma unroll
+            for (int k = 0; k < K; ++k) dst[k] = __ldg(row + k * 32);
+            dst[K] = __ldg(row + prev_off);
+        };
+        fetch(codes[clampi(-lane, 0, N - 1)], lutc);
+        int code_nx = codes[clampi(1 - lane, 0, N - 1)];
+        auto track_best = [&](const int j) {
+            float last = Sv[0];
+            if (!RL0) {
+#pragma unroll
+                for (int k = 1; k < K; ++k) last = (rlk == k) ? Sv[k * S] : last;
+            }
+            // strict >: first maximum wins (dp_scout.h:175); only the last lane's (best, bestj) is read afterwards
+            const bool upd = last > best;
+            best = upd ? last : best;
+            bestj = upd ? j : bestj;
+        };
+        auto store_ck = [&](const int j, const bool before) {   // checkpoint column j: H = S[j-1] + g_h (before), S (after)
+            const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = lane * R + r;
+                if (i >= 1 && i <= L) {
+                    if (before) ckH[o + r] = Sv[r] + gh; else ckS[o + r] = Sv[r];
+                }
+            }
+        };
+        // general step: any column (DP column 1, checkpoint columns, lanes outside [1, N])
+        auto general = [&](const int st) {
+            const int j = st - lane;
+            fetch(code_nx, lutn);
+            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
+            const float inS = __shfl_up_sync(0xffffffffu, botS, 1);
+            if (j > 0 && j <= N && lane < nl) {
+                const bool ck = (j & (ALIGN_CKPT - 1)) == 0;
+                if (ck) store_ck(j, true);
+                const float diag = diag_next;
+                diag_next = inS;
+                if (j == 1) botS = column<true>(Sv, lutc, diag, inS, gh, gv, lane0);
+                else botS = column<false>(Sv, lutc, diag, inS, gh, gv, lane0);
+                if (ck) store_ck(j, false);
+                track_best(j);
+            }
+#pragma unroll
+            for (int k = 0; k <= K; ++k) lutc[k] = lutn[k];
+            code_nx = code_nx2;
+        };
+        // steady step: every lane is at a column 2 <= j <= N (idle lanes >= nl compute on zeros)
+        const uint16_t *cptr = codes;
+        auto steady = [&](const int st, const float (&lc)[K + 1], float (&ln)[K + 1], auto with_ck) {
+            constexpr bool CK = decltype(with_ck)::value;
+            const int j = st - lane;
+            fetch(code_nx, ln);
+            const int code_nx2 = *cptr++;                           // reads at most 2 codes past the signal (padded buffer)
+            const float inS = __shfl_up_sync(0xffffffffu, botS, 1);
+            const bool ck = CK && (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
+            if (CK && ck) store_ck(j, true);
+            const float diag = diag_next;
+            diag_next = inS;
+            botS = column2(Sv, lc, diag, inS, gh2, gv, lane0);
+            if (CK && ck) store_ck(j, false);
+            track_best(j);
+            code_nx = code_nx2;
+        };
+        int s = 1;
+        for (; s <= nl && s <= last_step; ++s) general(s);
+        cptr = codes + max(s - lane + 1, 0);
+        while (s + 1 <= N) {
+            const int m = s & (ALIGN_CKPT - 1);
+            if (m >= nl && m <= ALIGN_CKPT - 2) {
+                // both steps of every pair stay inside [nl, ALIGN_CKPT - 1] (mod ALIGN_CKPT): no lane checkpoints
+                int pairs = min((ALIGN_CKPT - m) >> 1, (N - s + 1) >> 1);
+                for (; pairs > 0; --pairs, s += 2) {
+                    steady(s, lutc, lutn, std::false_type{});
+                    steady(s + 1, lutn, lutc, std::false_type{});
+                }
+            } else {
+                steady(s, lutc, lutn, std::true_type{});
+                steady(s + 1, lutn, lutc, std::true_type{});
+                s += 2;
+            }
+        }
+        for (; s <= last_step; ++s) general(s);
+    }
+};
+
 struct TaskGeom {
     int t, N, f, L, nl, lastlane, kL;
     const uint16_t *codes;
@@ -438,6 +621,47 @@ __global__ void __launch_bounds__(32) align_scan_kernel(AlignBatch b, AlignGroup
         if (lane == g.lastlane) {
             b.res[g.t].score = best;
             b.res[g.t].best_j = bestj;
+        }
+    }
+}
+
+// Pass 1 with LinSweep2 (linear gap costs, S even).
+template <int K, int S>
+__global__ void __launch_bounds__(32, ALIGN_WARPS_PER_SM_PACKED) align_scan2_kernel(AlignBatch b, AlignGroup grp) {
+    constexpr int R = K * S;
+    const int lane = threadIdx.x;
+    const float INF = STRIQUE_SEQAN_INF;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(b.queue + 0, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= grp.n_tasks) break;
+        const int t = grp.order[q];
+        const int sg = b.task_sig[t], f = b.task_flank[t];
+        const int N = (int)(b.sig_off[sg + 1] - b.sig_off[sg]);
+        const int L = (b.flank_off[f + 1] - b.flank_off[f]) * b.samples;
+        const float *col0 = b.col0 + (size_t)f * b.col0_stride;
+        const int nl = L / R + 1, lastlane = L / R, rlk = (L % R) / S;      // DP rows 0..L over the lanes
+        float Sv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r;
+            Sv[r] = i <= L ? col0[i] : 0.f;
+        }
+        const float diag0 = (lane > 0 && lane * R - 1 <= L) ? col0[lane * R - 1] : 0.f;
+        float best = INF;
+        int bestj = -1;
+        if (lane == lastlane && col0[L] > INF) { best = col0[L]; bestj = 0; }
+        float *ck = b.ckpt + b.ckpt_off[t];
+        if (rlk == 0)
+            LinSweep2<K, S>::template run<true>(b.codes + b.sig_off[sg], N, b.lut + (size_t)t * b.lut_task_stride, lane, nl,
+                                                b.p, Sv, diag0, rlk, best, bestj, ck, ck + b.ckpt_rows, b.ckpt_rows, L);
+        else
+            LinSweep2<K, S>::template run<false>(b.codes + b.sig_off[sg], N, b.lut + (size_t)t * b.lut_task_stride, lane, nl,
+                                                 b.p, Sv, diag0, rlk, best, bestj, ck, ck + b.ckpt_rows, b.ckpt_rows, L);
+        if (lane == lastlane) {
+            b.res[t].score = best;
+            b.res[t].best_j = bestj;
         }
     }
 }
@@ -640,6 +864,16 @@ __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGrou
 template <int K, int S>
 int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
     const bool lin = align_params_linear(b.p);
+    if constexpr (S % 2 == 0) {
+        if (lin && !getenv("STRIQUE_NO_PACKED_SCAN")) {
+            int grid = ctx->num_sms * ALIGN_WARPS_PER_SM_PACKED;
+            if (grid > g.n_tasks) grid = g.n_tasks;
+            align_scan2_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            return STRIQUE_OK;
+        }
+    }
     int grid = ctx->num_sms * (lin ? (getenv("STRIQUE_SCAN_WARPS") ? atoi(getenv("STRIQUE_SCAN_WARPS")) : ALIGN_WARPS_PER_SM_LINEAR) : ALIGN_WARPS_PER_SM);
     if (grid > g.n_tasks) grid = g.n_tasks;
     if (lin)
@@ -678,8 +912,9 @@ bool align_params_linear(const strique_align_params &p) {
 
 bool align_pick_kernel(int nlev, int samples, int *K, int *S) {
     if (samples == 6) {
+        // strictly more rows than the flank has: the packed scan (LinSweep2) also gives DP row 0 a place in lane 0
         for (int k = 2; k <= 10; ++k)
-            if (k * 32 >= nlev) { *K = k; *S = 6; return true; }
+            if (k * 32 > nlev) { *K = k; *S = 6; return true; }
     }
     const int rows = nlev * samples;
     const int ks[4] = {4, 8, 16, 32};

@@ -28,6 +28,10 @@ namespace strique {
 constexpr int ALIGN_CKPT = STRIQUE_ALIGN_CKPT;   // columns between DP-column checkpoints (power of two)
 constexpr int ALIGN_WARPS_PER_SM = 8;    // resident single-warp CTAs per SM for the scan
 constexpr int ALIGN_WARPS_PER_SM_LINEAR = 16;   // ... for the linear-gap scan (half the registers)
+#ifndef ALIGN_PACKED_WARPS
+#define ALIGN_PACKED_WARPS 16
+#endif
+constexpr int ALIGN_WARPS_PER_SM_PACKED = ALIGN_PACKED_WARPS;   // ... for the packed linear-gap scan (LinSweep2)
 
 struct AlignGroup {        // tasks sharing one (K, S) kernel instantiation
     int K, S;
