@@ -75,15 +75,20 @@ def test_noisy_int16_reads_both_strands_with_methylation(ctx, model_file, mod_mo
 
 
 def test_bundled_c9orf72_read(ctx, model_file):
-    """data/c9orf72.fast5, minus strand: documented offset 1633 / ticks 40758
-    (docs/installation/test.md:16); the remaining columns equal the oracle's."""
+    """data/c9orf72.fast5, minus strand.  Reference pins: the documented offset 1633 / ticks 40758
+    (docs/installation/test.md:16) exactly, the documented count / scores / log p to the doc's own precision (they
+    come from a revision that cannot be run here).  ORACLE-RELATIVE (parity unpinned by the reference): every column
+    equals the oracle pipeline's on this read, integers and alignment scores to the last bit."""
     raw = fast5.read_raw_signal(os.path.join(ROOT, 'data', 'c9orf72.fast5'))
     cols = open(os.path.join(ROOT, 'configs', 'repeat_config.tsv')).read().split('\n')[1].split()
     dt = repeatCounter(model_file, context=ctx)
     dt.add_target(cols[3], cols[4], cols[5], cols[6])
     got = dt.detect('c9orf72', raw, '-')
     assert got[4] == 1633 and got[5] == 40758
-    assert got[0] == 733
-    assert got[1] == 6.358286602121677 and got[2] == 6.086084196539416
-    assert got[3] == pytest.approx(-121549.34988420883, rel=1e-9)
+    assert abs(got[0] - 735) <= 2
+    assert got[1] == pytest.approx(6.3155927807600545, rel=0.015) and got[2] == pytest.approx(6.031860427335506, rel=0.015)
+    assert got[3] == pytest.approx(-119860.52066647023, rel=0.02)
     assert got[6] == '-'
+    ref = rp.RefRepeatCounter(model_file)
+    ref.add_target(cols[3], cols[4], cols[5], cols[6])
+    _same(got, ref.detect('c9orf72', raw, '-'))
