@@ -6,10 +6,16 @@
 
 Same arguments, same `repeat_config.tsv` / pore model / JSON inputs, same ten TSV columns.  What is
 different underneath: SAM records are decoded and intersected with the loci on the host (as in
-repeatDetector, scripts/STRique.py:624-705), the raw signals are fetched by `--t` I/O threads, and
-reads go to the GPU in batches through `repeatCounter.detect_batch` (strique_detect_batch).  Rows are
-written in input order.  Launched under `torchrun --nproc-per-node N` every rank takes a
-cost-balanced share of the reads on its own GPU and rank 0 gathers the rows (strique_b200/sharding.py).
+repeatDetector, scripts/STRique.py:624-705), the raw signals are fetched by `--t` I/O threads running ahead of
+the GPU (bounded by the size of one batch), and reads go to the GPU in batches through
+`repeatCounter.detect_batch` (strique_detect_batch).
+
+Streaming, like the reference (scripts/STRique.py:720-727, 936-945): the SAM is consumed as it arrives (a pipe on
+stdin works) and the rows of a batch are appended to the output as soon as the batch is done, so partial output
+survives a crash.  Row order is INPUT order (the reference writes in completion order, which is not reproducible
+for --t > 1).  Launched under `torchrun --nproc-per-node N`, rank 0 alone reads the SAM, plans it in chunks and
+broadcasts every chunk; each rank decodes a cost-balanced share of the chunk on its own GPU and rank 0 gathers and
+writes the chunk's rows (strique_b200/sharding.py).
 """
 import argparse
 import json
@@ -18,7 +24,7 @@ import re
 import signal
 import sys
 import time
-from collections import defaultdict
+from collections import defaultdict, deque
 from concurrent.futures import ThreadPoolExecutor
 
 from . import fast5, sharding
@@ -102,8 +108,11 @@ def decode_sam(sam_line):
 class repeatDetector(object):
     """Multi-locus repeat detection over SAM records (scripts/STRique.py:624-705), batched."""
 
+    # samples per signal base, for planning before a read is fetched (450 bases/s at 4 kHz)
+    SAMPLES_PER_BASE = 9
+
     def __init__(self, repeat_config, model_file, fast5_index_file, mod_model_file=None, align_config=None,
-                 HMM_config=None, device=0, io_threads=1, batch_samples=96 << 20, counter=None):
+                 HMM_config=None, device=0, io_threads=1, batch_samples=None, counter=None):
         from .counter import repeatCounter
         self.repeatCounter = counter or repeatCounter(model_file, mod_model_file=mod_model_file,
                                                       align_config=align_config, HMM_config=HMM_config, device=device)
@@ -112,7 +121,8 @@ class repeatDetector(object):
         self.is_init = False
         self.f5 = fast5.fast5Index(fast5_index_file)
         self.io_threads = max(int(io_threads), 1)
-        self.batch_samples = int(batch_samples)
+        # samples per GPU batch: ~8 k reads of 45 k samples (0.8 GB of int16 on the host and on the device)
+        self.batch_samples = int(batch_samples or os.environ.get('STRIQUE_BATCH_SAMPLES', 384 << 20))
 
     def __init_hmm__(self):
         for target_name, (chrom, begin, end, repeat, prefix, suffix) in self.repeat_config.items():
@@ -128,11 +138,10 @@ class repeatDetector(object):
                 names.append(target_name)
         return names
 
-    def plan(self, sam_lines):
-        """-> list of (input index, sam_record, strand, [target names]) for the records that hit a locus."""
+    def plan_iter(self, sam_lines):
+        """Lazily: (input index, sam_record, strand, [target names]) for the records that hit a locus."""
         if not self.is_init:
             self.__init_hmm__()
-        work = []
         for idx, line in enumerate(sam_lines):
             sr = decode_sam(line)
             if not sr.QNAME:
@@ -142,8 +151,10 @@ class repeatDetector(object):
             if not names:
                 logger.log('Detector: No target for {}'.format(sr.QNAME), 'debug')
                 continue
-            work.append((idx, sr, '-' if sr.FLAG & 0x10 else '+', names))
-        return work
+            yield (idx, sr, '-' if sr.FLAG & 0x10 else '+', names)
+
+    def plan(self, sam_lines):
+        return list(self.plan_iter(sam_lines))
 
     def _fetch(self, item):
         idx, sr, strand, names = item
@@ -170,11 +181,30 @@ class repeatDetector(object):
             if res is not None:
                 rows.append((idx, (sr.QNAME, name, strand) + tuple(res)))
 
-    def detect_records(self, work):
-        """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""
-        rows, batch, samples = [], [], 0
+    def detect_stream(self, work_iter, emit):
+        """work_iter: items of plan_iter() (possibly one rank's share); emit(rows) is called once per GPU batch with
+        that batch's (input index, row tuple) list, in input order.  Fetches run ahead of the GPU on the I/O threads,
+        at most one batch worth of (estimated) samples ahead -- fetched signals never pile up unbounded."""
+        pending = deque()                      # (item, future, estimated samples)
+        ahead = 0
+        batch, samples = [], 0
+        work_iter = iter(work_iter)
+        exhausted = False
         with ThreadPoolExecutor(self.io_threads) as pool:
-            for item, raw in pool.map(self._fetch, work):
+            while True:
+                while not exhausted and (ahead < self.batch_samples or not pending):
+                    item = next(work_iter, None)
+                    if item is None:
+                        exhausted = True
+                        break
+                    est = max(item[1].SEQ_LEN, 1) * self.SAMPLES_PER_BASE * len(item[3])
+                    pending.append((item, pool.submit(self._fetch, item), est))
+                    ahead += est
+                if not pending:
+                    break
+                item, fut, est = pending.popleft()
+                ahead -= est
+                _, raw = fut.result()
                 if raw is None:
                     logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
                     continue
@@ -182,10 +212,19 @@ class repeatDetector(object):
                     batch.append((item, raw, name))
                     samples += len(raw)
                 if samples >= self.batch_samples:
-                    self._flush(batch, rows)
+                    rows = []
+                    self._flush(batch, rows)   # the I/O threads keep fetching the next batch meanwhile
+                    emit(rows)
                     batch, samples = [], 0
         if batch:
+            rows = []
             self._flush(batch, rows)
+            emit(rows)
+
+    def detect_records(self, work):
+        """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""
+        rows = []
+        self.detect_stream(work, rows.extend)
         return rows
 
     def detect(self, sam_line=''):
@@ -208,6 +247,7 @@ class outputWriter(object):
     def write_line(self, target_counts=()):
         for target_count in target_counts:
             print('\t'.join([str(x) for x in target_count]), file=self.fp)
+        self.fp.flush()                        # rows reach the file batch by batch (S.py:720-724 appends per read)
 
     def close(self):
         if self.output_file:
@@ -273,23 +313,64 @@ Available commands are:
         device = int(os.environ.get('LOCAL_RANK', 0))
         rd = repeatDetector(config['repeat'], args.model, args.f5Index, mod_model_file=args.mod_model,
                             align_config=config['align'], HMM_config=config['HMM'], device=device, io_threads=args.t)
-        if args.algn:
-            with open(args.algn, 'r') as fp:
-                sam_lines = [line for line in fp if not line.startswith('@')]
-        else:
-            sam_lines = [line for line in sys.stdin if not line.startswith('@')]
-        work = rd.plan(sam_lines)
+        # under torchrun only rank 0 reads the SAM: a pipe on stdin reaches one process
+        lines = None
+        if rank == 0:
+            lines = (line for line in (open(args.algn, 'r') if args.algn else sys.stdin) if not line.startswith('@'))
+        run_count(rd, lines, args.out, rank, world)
+        sharding.finalize()
+
+
+def run_count(rd, lines, out, rank=0, world=1):
+    """The body of `count`: SAM lines (rank 0's iterator; None on the other ranks) -> TSV rows, streamed batch by
+    batch in input order.  One process: plan -> fetch ahead -> GPU batch -> append rows.  Several ranks: rank 0 plans
+    chunks of about one batch per rank and broadcasts each; the ranks decode their cost-balanced shares and rank 0
+    gathers and writes the chunk's rows before the next chunk is dealt."""
+    t0 = time.time()
+    n_rows = 0
+    if not rd.is_init:
+        rd.__init_hmm__()
+    if world == 1:
+        ow = outputWriter(out)
+
+        def emit(rows):
+            nonlocal n_rows
+            n_rows += len(rows)
+            ow.write_line([r for _, r in rows])
+            logger.log('Main: {} rows after {:.2f} s'.format(n_rows, time.time() - t0), 'info')
+
+        rd.detect_stream(rd.plan_iter(lines), emit)
+        ow.close()
+        return n_rows
+    ow = outputWriter(out) if rank == 0 else None
+    plan = rd.plan_iter(lines) if rank == 0 else None
+    chunk_samples = rd.batch_samples * world
+    while True:
+        work = None
+        if rank == 0:
+            work, est = [], 0
+            for item in plan:
+                work.append(item)
+                est += max(item[1].SEQ_LEN, 1) * rd.SAMPLES_PER_BASE * len(item[3])
+                if est >= chunk_samples:
+                    break
+            if not work:
+                work = None
+        work = sharding.broadcast_object(work)
+        if work is None:
+            break
         # cost of a read ~ its length (2 flank alignments over the whole signal dominate)
         shards = sharding.lpt_partition([w[1].SEQ_LEN * len(w[3]) for w in work], world)
-        t0 = time.time()
         rows = rd.detect_records([work[i] for i in shards[rank]])
-        logger.log('Main: rank {} processed {} reads in {:.2f} s'.format(rank, len(shards[rank]), time.time() - t0), 'info')
         rows = sharding.gather_rows(rows)
         if rank == 0:
-            ow = outputWriter(args.out)
+            n_rows += len(rows)
             ow.write_line([r for _, r in rows])
-            ow.close()
-        sharding.finalize()
+            logger.log('Main: {} rows after {:.2f} s'.format(n_rows, time.time() - t0), 'info')
+    if rank == 0:
+        ow.close()
+    logger.log('Main: rank {} done in {:.2f} s'.format(rank, time.time() - t0), 'info')
+    return n_rows
 
 
 def run():

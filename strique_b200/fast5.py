@@ -11,13 +11,16 @@ superblock v0/v1, v1 object headers (+ continuation blocks), old-style groups (s
 B-tree v1 / SNOD / local heap), compact new-style groups (link messages), chunked (B-tree v1),
 contiguous or compact datasets of fixed-point integers, deflate and shuffle filters.
 """
+import mmap
 import os
 import sys
 import re
 import struct
 import tarfile
 import tempfile
+import threading
 import zlib
+from collections import OrderedDict
 
 import numpy as np
 
@@ -37,8 +40,14 @@ class _MiniHDF5:
     """Read-only subset HDF5 reader (see module docstring)."""
 
     def __init__(self, path):
+        # memory-mapped: a multi-read file holds thousands of reads in hundreds of megabytes, and one read touches
+        # a few object headers and its own chunks
         with open(path, 'rb') as fp:
-            self.buf = fp.read()
+            try:
+                self.buf = mmap.mmap(fp.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:               # empty file
+                self.buf = b''
+        self._links = {}                     # group address -> members (parsed once per open file)
         b = self.buf
         base = 0
         while b[base:base + 8] != b'\x89HDF\r\n\x1a\n':
@@ -92,7 +101,7 @@ class _MiniHDF5:
         if self.buf[h:h + 4] != b'HEAP':
             raise HDF5Error('bad local heap')
         data = self._u(h + 24, 8) + self.base
-        e = self.buf.index(b'\0', data + off)
+        e = self.buf.find(b'\0', data + off)
         return self.buf[data + off:e].decode('utf-8')
 
     def _walk_group_btree(self, node_addr, heap_addr, out):
@@ -115,7 +124,9 @@ class _MiniHDF5:
 
     def links(self, addr):
         """name -> object header address of every member of the group at `addr`."""
-        out = {}
+        if addr in self._links:
+            return self._links[addr]
+        out = self._links[addr] = {}
         for mtype, _, d in self._messages(addr):
             if mtype == 0x11:     # symbol table message: B-tree v1 + local heap
                 self._walk_group_btree(self._u_b(d, 0, 8), self._u_b(d, 8, 8), out)
@@ -215,8 +226,7 @@ class _MiniHDF5:
         """Depth-first search below `raw_group_path` for the first member whose path contains
         'Signal' (the reference uses h5py `visit`, fast5Index.py:80)."""
         def visit(addr):
-            for name in sorted(self.links(addr)):
-                child = self.links(addr)[name]
+            for name, child in sorted(self.links(addr).items()):
                 if 'Signal' in name:
                     return child
                 try:
@@ -317,12 +327,38 @@ class _MiniHDF5:
                     raw = arr[:cnt * es].reshape(es, cnt).T.tobytes() + arr[cnt * es:].tobytes()
                 elif fid == 3:
                     raw = raw[:-4]
+                elif fid == 32020:
+                    raise HDF5Error('VBZ-compressed signal (HDF5 filter 32020): decoding needs h5py with the ont-vbz '
+                                    'plugin (neither zstd nor h5py is available to this reader); recompress the file '
+                                    'with `compress_fast5 --compression gzip`')
                 else:
-                    raise HDF5Error('HDF5 filter {} (e.g. VBZ=32020) needs h5py plus its plugin'.format(fid))
+                    raise HDF5Error('HDF5 filter {} is not supported by the built-in reader'.format(fid))
             vals = np.frombuffer(raw, dtype=dtype, count=min(clen, len(raw) // dtype.itemsize))
             take = min(len(vals), out.shape[0] - off0)
             if take > 0:
                 out[off0:off0 + take] = vals[:take]
+
+
+_open_lock = threading.Lock()
+_open_files = OrderedDict()          # path -> (mtime, size, _MiniHDF5): the most recently used files stay mapped
+_OPEN_MAX = 16
+
+
+def _open(path):
+    st = os.stat(path)
+    key = (st.st_mtime_ns, st.st_size)
+    with _open_lock:
+        hit = _open_files.get(path)
+        if hit is not None and hit[0] == key:
+            _open_files.move_to_end(path)
+            return hit[1]
+    f = _MiniHDF5(path)
+    with _open_lock:
+        _open_files[path] = (key, f)
+        _open_files.move_to_end(path)
+        while len(_open_files) > _OPEN_MAX:
+            _open_files.popitem(last=False)
+    return f
 
 
 def read_raw_signal(f5_file, offset=''):
@@ -333,7 +369,7 @@ def read_raw_signal(f5_file, offset=''):
         with _h5py.File(f5_file, 'r') as fp:
             s = fp[raw_group].visit(lambda name: name if 'Signal' in name else None)
             return fp[raw_group + '/' + s][()]
-    f = _MiniHDF5(f5_file)
+    f = _open(f5_file)
     addr = f.find_signal(raw_group)
     if addr is None:
         raise HDF5Error('no Signal dataset below ' + raw_group)
@@ -348,7 +384,7 @@ def read_id_of(f5_file, offset=''):
             s = fp[raw_group].visit(lambda name: name if 'Signal' in name else None)
             rid = fp[raw_group + '/' + s.rpartition('/')[0]].attrs['read_id']
             return rid.decode('utf-8') if isinstance(rid, bytes) else str(rid)
-    f = _MiniHDF5(f5_file)
+    f = _open(f5_file)
     found = f.find_signal_path(raw_group)
     if found is None:
         raise HDF5Error('no Signal dataset below ' + raw_group)
@@ -359,7 +395,7 @@ def top_level_groups(f5_file):
     if _h5py is not None:  # pragma: no cover
         with _h5py.File(f5_file, 'r') as fp:
             return list(fp)
-    f = _MiniHDF5(f5_file)
+    f = _open(f5_file)
     return sorted(f.links(f.root))
 
 
@@ -422,8 +458,8 @@ class fast5Index(object):
     def _get_raw(self, f5_file, ID, offset=''):
         try:
             return read_raw_signal(f5_file, offset)
-        except Exception:  # noqa: BLE001 - same catch-all as the reference
-            raise RuntimeError('[ERROR] Could not retrieve {ID} from file {file}.'.format(ID=ID, file=f5_file))
+        except Exception as e:  # noqa: BLE001 - same catch-all as the reference (the cause is appended)
+            raise RuntimeError('[ERROR] Could not retrieve {ID} from file {file}. ({why})'.format(ID=ID, file=f5_file, why=e))
 
     def get_raw(self, ID):
         assert self.index_dict
@@ -436,6 +472,9 @@ class fast5Index(object):
             return self._get_raw(os.path.join(self.index_dir, target[0] + '.fast5'), ID, offset=target[2])
         with tempfile.TemporaryDirectory(prefix=self.tmp_prefix) as tmp, \
                 tarfile.open(os.path.join(self.index_dir, target[0] + '.tar')) as tar:
-            member = tar.getmember(target[2])
+            try:
+                member = tar.getmember(target[2])
+            except KeyError:                  # archives made with `tar -cf x.tar .` name their members ./path
+                member = tar.getmember('./' + target[2])
             tar.extract(member, path=tmp)
             return self._get_raw(os.path.join(tmp, member.name), ID)

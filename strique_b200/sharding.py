@@ -43,6 +43,17 @@ def init_host_group(backend='gloo'):
     return rank, world
 
 
+def broadcast_object(obj, src=0):
+    """Every rank gets rank `src`'s object (the CLI's work lists: only rank 0 reads the SAM)."""
+    _, world = rank_and_world()
+    if world <= 1:
+        return obj
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def gather_rows(local_rows, dst=0):
     """local_rows: list of (input index, row).  Rank `dst` gets all rows sorted by input index, the
     other ranks None."""

@@ -1,5 +1,6 @@
 """Worker of tests/test_sharding_gloo.py: one rank of a world_size-2 `gloo` job running the CLI's
-host logic (plan -> shard -> detect -> gather) with a stub in place of the CUDA repeatCounter."""
+host logic (cli.run_count: rank 0 streams and plans the SAM, broadcasts chunks; shard -> detect -> gather -> append)
+with a stub in place of the CUDA repeatCounter."""
 import os
 import sys
 
@@ -56,15 +57,10 @@ def main():
     rd.is_init = False
     rd.f5 = StubIndex()
     rd.io_threads = 2
-    rd.batch_samples = 20000
-    work = rd.plan(sam_lines(60))
-    shards = sharding.lpt_partition([w[1].SEQ_LEN * len(w[3]) for w in work], world)
-    rows = rd.detect_records([work[i] for i in shards[rank]])
-    rows = sharding.gather_rows(rows)
-    if rank == 0:
-        ow = cli.outputWriter(out_file)
-        ow.write_line([r for _, r in rows])
-        ow.close()
+    rd.batch_samples = 20000                # several batches per rank and several chunks per run
+    # like a pipe on stdin: ONLY rank 0 has the SAM lines (the others get None), rank 0 broadcasts the planned chunks
+    lines = iter(sam_lines(60)) if rank == 0 else None
+    cli.run_count(rd, lines, out_file if rank == 0 else None, rank, world)
     sharding.finalize()
 
 

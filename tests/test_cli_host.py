@@ -75,3 +75,86 @@ def test_output_writer_format(tmp_path):
     assert lines[0] == 'ID\ttarget\tstrand\tcount\tscore_prefix\tscore_suffix\tlog_p\toffset\tticks\tmod'
     assert lines[1] == 'id1\tc9orf72\t-\t735\t6.3155927807600545\t6.031860427335506\t-119860.52066647023\t1633\t40758\t-'
     assert lines[2] == 'id2\tc9orf72\t+\t0\t0.0\t0.0\t0\t12\t0\t-'
+
+
+def _stub_detector(batch_samples, fetch_log=None, fail_ids=()):
+    """repeatDetector with a stub counter and a stub index (the host logic of `count` without a GPU)"""
+    from collections import defaultdict
+
+    class Counter(object):
+        def __init__(self):
+            self.targets, self.batches = {}, []
+
+        def add_target(self, name, *a):
+            self.targets[name] = a
+
+        def detect_batch(self, items):
+            self.batches.append(len(items))
+            return [(len(sig) % 997, 1.5, 2.5, -1.0, 10, 20, '-') for _, sig, _ in items]
+
+    class Index(object):
+        def get_raw(self, ID):
+            if fetch_log is not None:
+                fetch_log.append(ID)
+            if ID in fail_ids:
+                raise RuntimeError('[Error] Read {} not found'.format(ID))
+            return np.zeros(1000 + int(ID[4:]), dtype=np.int16)
+
+    rd = cli.repeatDetector.__new__(cli.repeatDetector)
+    rd.repeatCounter, rd.f5 = Counter(), Index()
+    rd.repeatLoci, rd.repeat_config, rd.is_init = defaultdict(list), cli.parse_config(CONFIG_TSV)['repeat'], False
+    rd.io_threads, rd.batch_samples = 2, batch_samples
+    return rd
+
+
+def _sam(i):
+    return '\t'.join(['read%03d' % i, '16' if i % 2 else '0', 'chr9', '27573000', '60', '1000M', '*', '0', '0', 'A' * 100, '*']) + '\n'
+
+
+def test_count_streams_input_and_appends_rows_batch_by_batch(tmp_path):
+    """scripts/STRique.py:720-727, 936-945: the SAM is consumed as it arrives and rows reach the output while later
+    reads are still to come -- partial output survives a crash.  Here: rows of the first batches are in the file
+    before the input iterator is exhausted, fetching runs at most about one batch ahead, rows are in input order,
+    and a read without a fast5 is dropped with a warning like in the reference."""
+    out = tmp_path / 'o.tsv'
+    fetched = []
+    rd = _stub_detector(batch_samples=10 * 1050, fetch_log=fetched, fail_ids={'read007'})
+    seen_at_yield = []
+
+    def lines():
+        for i in range(60):
+            if i % 5 == 0:
+                seen_at_yield.append((i, out.read_text().count('\n') - 1 if out.exists() else 0, len(fetched)))
+            yield _sam(i)
+        yield 'garbage\n'
+
+    n = cli.run_count(rd, lines(), str(out))
+    rows = out.read_text().strip().split('\n')[1:]
+    assert n == len(rows) == 59
+    ids = [r.split('\t')[0] for r in rows]
+    assert ids == sorted(ids) and 'read007' not in ids
+    assert len(rd.repeatCounter.batches) >= 5                                 # many GPU batches ...
+    assert any(written > 0 for i, written, _ in seen_at_yield if i < 55)      # ... whose rows were on disk mid-stream
+    # bounded prefetch: when line i is pulled, at most ~one batch (SEQ_LEN 100 * 9 = 900 estimated samples per read:
+    # 12 reads) plus the pool's slack has been fetched beyond what was consumed
+    assert all(nf <= i + 1 for i, _, nf in seen_at_yield)
+    assert max(i - w for i, w, _ in seen_at_yield) <= 30
+
+
+def test_failing_batch_is_retried_read_by_read(tmp_path):
+    rd = _stub_detector(batch_samples=1 << 30)
+    calls = []
+
+    def detect_batch(items):
+        calls.append(len(items))
+        if len(items) > 1:
+            raise RuntimeError('boom')
+        if items[0][1].shape[0] == 1003:
+            raise RuntimeError('bad read')
+        return [(1, 1.0, 1.0, -1.0, 1, 1, '-')]
+
+    rd.repeatCounter.detect_batch = detect_batch
+    rd.repeatCounter.detect = lambda *it: detect_batch([it])[0]
+    out = tmp_path / 'o.tsv'
+    assert cli.run_count(rd, iter([_sam(i) for i in range(6)]), str(out)) == 5   # read003 is dropped, the rest survive
+    assert calls[0] == 6 and calls.count(1) == 6
