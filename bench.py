@@ -62,6 +62,9 @@ def parse_args():
                          '--dataset reads partitioned over the ranks by cost (strique_b200.sharding), rows gathered on rank 0')
     ap.add_argument('--dataset', type=int, default=65536, help='reads of the strong-scaling dataset')
     ap.add_argument('--exact', action='store_true', help='float64 Viterbi only (strique_set_viterbi_exact)')
+    ap.add_argument('--cli-reads', type=int, default=10240,
+                    help='reads of the CLI end-to-end measurement (`scripts/STRique.py count` on a synthetic multi-read '
+                         'fast5 data set); 0 skips it')
     args = ap.parse_args()
     if args.mod and args.workload == 'c2':
         args.workload = 'c3'
@@ -278,6 +281,51 @@ def reference_main(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def cli_e2e(args, n_reads):
+    """`scripts/STRique.py count` as a user runs it: index of multi-read fast5 files + SAM on disk -> TSV, wall clock of
+    the whole process (interpreter start, CUDA context, HMM build, fast5 decode in --t worker processes, GPU batches,
+    row writing).  The data set is written first (untimed).  -> dict for the JSON line"""
+    import shutil
+    import subprocess
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import make_fast5_dataset as mk
+    tmp = tempfile.mkdtemp(prefix='strique_cli_')
+    try:
+        t0 = time.time()
+        reads = make_workload(args, range(n_reads), seed=1000)
+        index_file, sam_file, _ = mk.build(tmp, reads)
+        t_make = time.time() - t0
+        cores = os.cpu_count() or 1
+        cmd = [sys.executable, os.path.join(ROOT, 'scripts', 'STRique.py'), 'count', index_file, MODEL,
+               os.path.join(ROOT, 'configs', 'panel_config.tsv'), '--algn', sam_file, '--t', str(min(cores, 32)),
+               '--out', os.path.join(tmp, 'out.tsv')]
+        if args.mod:
+            cmd += ['--mod_model', MOD_MODEL]
+        # start-up alone (empty SAM): interpreter, CUDA context, HMMs of the panel
+        empty = os.path.join(tmp, 'empty.sam')
+        open(empty, 'w').write('@HD\tVN:1.6\n')
+        t0 = time.time()
+        subprocess.run(cmd[:cmd.index('--algn') + 1] + [empty] + cmd[cmd.index('--algn') + 2:], check=True, capture_output=True)
+        t_start = time.time() - t0
+        t0 = time.time()
+        subprocess.run(cmd, check=True, capture_output=True)
+        wall = time.time() - t0
+        rows = open(os.path.join(tmp, 'out.tsv')).read().strip().split('\n')[1:]
+        truth = {('synth-%08d' % k): r[3] for k, r in enumerate(reads)}
+        exact = sum(1 for r in rows if int(r.split('\t')[3]) == truth[r.split('\t')[0]])
+        fast5_mb = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.endswith('.fast5')) / 1e6
+        return {'value': n_reads / wall, 'unit': 'reads/s', 'reads': n_reads, 'wall_s': wall, 'startup_s': t_start,
+                'value_after_startup': n_reads / max(wall - t_start, 1e-9), 'io_workers': min(cores, 32),
+                'rows': len(rows), 'count_exact': exact, 'fast5_mb': fast5_mb, 'dataset_build_s': t_make,
+                'what': 'scripts/STRique.py count <index> <model> <panel_config> --algn <sam> --t <workers> --out <tsv> on '
+                        'multi-read fast5 files (deflate), wall clock of the process'}
+    except Exception as e:  # noqa: BLE001 - the hot-path numbers above must survive a failure here
+        return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def init_distributed(local_rank, world):
     """NCCL process group for the plumbing (barrier, max-over-ranks of the timings); no collective on the data path."""
     import torch
@@ -493,6 +541,8 @@ def main():
             mism = sum(1 for k in range(n_sample)
                        if (int(cpu_res[k][0]), int(cpu_res[k][4]), int(cpu_res[k][5])) !=
                        (int(res['count'][k]) if res['hmm_ran'][k] else 0, int(res['offset'][k]), int(res['ticks'][k])))
+            if args.cli_reads > 0:
+                line['cli_e2e'] = cli_e2e(args, args.cli_reads)
             line['cpu_baseline'] = {'value': n_sample / wall, 'unit': 'reads/s', 'cores': min(cores, n_sample),
                                     'kind': cpu_kind(),
                                     'sample': 'first %d reads of the step, workers pull reads longest first, %.1f s wall'

@@ -257,6 +257,12 @@ int strique_detect_batch(strique_ctx *ctx, const strique_detect_config *cfg, int
 
 int64_t strique_last_mod_bytes(const strique_ctx *ctx);
 
+/* Page-locked host memory for the caller's batch staging buffers (raw of strique_detect_batch with STRIQUE_HOST):
+ * the read-batching driver writes decoded fast5 signals straight into it (the reference hands numpy arrays from
+ * h5py to its workers, STRique_lib/fast5Index.py:76-84).  NULL when the allocation fails. */
+void *strique_host_alloc(size_t bytes);
+void strique_host_free(void *p);
+
 /* device time of the stages of the last strique_detect_batch call (ms) */
 #define STRIQUE_STAGE_CONDITION 0
 #define STRIQUE_STAGE_ALIGN_TABLE 1

@@ -128,6 +128,10 @@ def load():
     lib.strique_last_viterbi_declined.argtypes = [c_void_p]
     lib.strique_set_viterbi_exact.restype = c_int
     lib.strique_set_viterbi_exact.argtypes = [c_void_p, c_int]
+    lib.strique_host_alloc.restype = c_void_p
+    lib.strique_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.strique_host_free.restype = None
+    lib.strique_host_free.argtypes = [c_void_p]
     lib.strique_last_mod_bytes.restype = c_int64
     lib.strique_last_mod_bytes.argtypes = [c_void_p]
     lib.strique_last_stage_ms.restype = ctypes.c_float
@@ -342,6 +346,27 @@ class Context:
     def last_viterbi_fixed(self):
         """(sequences decoded in fixed point, sequences handed on to the float64 kernel) of the last call"""
         return (int(self.lib.strique_last_viterbi_fixed(self.handle)), int(self.lib.strique_last_viterbi_declined(self.handle)))
+
+
+class PinnedBuffer(object):
+    """numpy view over page-locked host memory (strique_host_alloc); freed with the object."""
+
+    def __init__(self, n, dtype=np.int16):
+        self.lib = load()
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        self.ptr = self.lib.strique_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise StriqueError('strique_host_alloc of {} bytes failed'.format(self.nbytes))
+        self.array = np.frombuffer((ctypes.c_char * self.nbytes).from_address(self.ptr), dtype=dtype)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ptr', None):
+                self.array = None
+                self.lib.strique_host_free(self.ptr)
+                self.ptr = None
+        except Exception:  # noqa: BLE001
+            pass
 
 
 _default_ctx = {}

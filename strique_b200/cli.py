@@ -25,7 +25,9 @@ import signal
 import sys
 import time
 from collections import defaultdict, deque
-from concurrent.futures import ThreadPoolExecutor
+from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor
+
+import numpy as np
 
 from . import fast5, sharding
 
@@ -105,6 +107,51 @@ def decode_sam(sam_line):
     return sr
 
 
+# ---- fast5 decoding in worker PROCESSES (--t > 1): the HDF5 walk is Python and holds the GIL, only zlib does not --
+_worker_index = None
+
+
+def _worker_init(index_file):
+    global _worker_index
+    signal.signal(signal.SIGINT, signal.SIG_IGN)
+    _worker_index = fast5.fast5Index(index_file)
+
+
+def _worker_fetch(read_id):
+    try:
+        return _worker_index.get_raw(read_id), None
+    except Exception as e:  # noqa: BLE001 - a bad read must not stop the others (S.py:764-768)
+        return None, str(e)
+
+
+class _Staging(object):
+    """Reads of one GPU batch back to back in ONE page-locked int16 buffer: decoded signals are copied in as they
+    arrive and the batch goes to strique_detect_batch without another concatenation, at pinned-memory PCIe speed."""
+
+    def __init__(self, capacity):
+        from . import _lib
+        self._lib = _lib
+        self.buf = _lib.PinnedBuffer(capacity, np.int16)
+        self.reset()
+
+    def reset(self):
+        self.meta, self.offsets, self.pos = [], [0], 0
+
+    def fits(self, n):
+        return self.pos + n <= len(self.buf.array)
+
+    def grow(self, n):
+        """an empty buffer too small for one read"""
+        self.buf = self._lib.PinnedBuffer(n + (n >> 2), np.int16)
+
+    def add(self, item, name, raw):
+        n = len(raw)
+        self.buf.array[self.pos:self.pos + n] = raw
+        self.pos += n
+        self.offsets.append(self.pos)
+        self.meta.append((item, name))
+
+
 class repeatDetector(object):
     """Multi-locus repeat detection over SAM records (scripts/STRique.py:624-705), batched."""
 
@@ -164,7 +211,13 @@ class repeatDetector(object):
             logger.log('Detector: {}'.format(e), 'warning')
             return item, None
 
+    def _rows(self, meta, results, rows):
+        for ((idx, sr, strand, _), name), res in zip(meta, results):
+            if res is not None:
+                rows.append((idx, (sr.QNAME, name, strand) + tuple(res)))
+
     def _flush(self, batch, rows):
+        """batch: list of ((item), raw, name) -- the generic path (any signal dtype, any counter)"""
         items = [(name, raw, strand) for (_, _, strand, _), raw, name in batch]
         try:
             results = self.repeatCounter.detect_batch(items)
@@ -177,20 +230,75 @@ class repeatDetector(object):
                 except Exception as e2:  # noqa: BLE001
                     logger.log('Detector: read failed: {}'.format(e2), 'warning')
                     results.append(None)
-        for ((idx, sr, strand, _), _, name), res in zip(batch, results):
-            if res is not None:
-                rows.append((idx, (sr.QNAME, name, strand) + tuple(res)))
+        self._rows([(item, name) for item, _, name in batch], results, rows)
+
+    def _flush_staged(self, st, rows):
+        """st: _Staging -- the int16 path: no per-batch concatenation, pinned upload"""
+        targets = [(name, item[2]) for item, name in st.meta]
+        raw = st.buf.array[:st.pos]
+        try:
+            results = self.repeatCounter.detect_packed(targets, raw, st.offsets)
+        except Exception as e:  # noqa: BLE001 - isolate the failing read
+            logger.log('Detector: batch of {} reads failed ({}); retrying read by read'.format(len(targets), e), 'warning')
+            results = []
+            for k, (name, strand) in enumerate(targets):
+                try:
+                    results.append(self.repeatCounter.detect(name, raw[st.offsets[k]:st.offsets[k + 1]].copy(), strand))
+                except Exception as e2:  # noqa: BLE001
+                    logger.log('Detector: read failed: {}'.format(e2), 'warning')
+                    results.append(None)
+        self._rows(st.meta, results, rows)
+        st.reset()
+
+    def _pool(self):
+        """--t worker processes decoding fast5 (each loads the index itself), or threads for --t 1 / a stub index /
+        STRIQUE_IO_THREADS=1.  -> (executor, submit(item) -> future of (item, raw or None))"""
+        index_file = getattr(self.f5, 'index_file', None)
+        if self.io_threads > 1 and index_file and not os.environ.get('STRIQUE_IO_THREADS'):
+            import multiprocessing as mp
+            pool = ProcessPoolExecutor(self.io_threads, mp_context=mp.get_context('spawn'), initializer=_worker_init,
+                                       initargs=(index_file,))
+
+            def submit(item):
+                fut = pool.submit(_worker_fetch, item[1].QNAME)
+                fut.item = item
+                return fut
+
+            def result(fut):
+                raw, err = fut.result()
+                if err:
+                    logger.log('Detector: {}'.format(err), 'warning')
+                return fut.item, raw
+            return pool, submit, result
+        pool = ThreadPoolExecutor(self.io_threads)
+        return pool, (lambda item: pool.submit(self._fetch, item)), (lambda fut: fut.result())
 
     def detect_stream(self, work_iter, emit):
         """work_iter: items of plan_iter() (possibly one rank's share); emit(rows) is called once per GPU batch with
-        that batch's (input index, row tuple) list, in input order.  Fetches run ahead of the GPU on the I/O threads,
+        that batch's (input index, row tuple) list, in input order.  Fetches run ahead of the GPU on the I/O workers,
         at most one batch worth of (estimated) samples ahead -- fetched signals never pile up unbounded."""
         pending = deque()                      # (item, future, estimated samples)
         ahead = 0
         batch, samples = [], 0
+        staged = None                          # _Staging once the first int16 signal has arrived
+        can_stage = hasattr(self.repeatCounter, 'detect_packed')
         work_iter = iter(work_iter)
         exhausted = False
-        with ThreadPoolExecutor(self.io_threads) as pool:
+        pool, submit, result = self._pool()
+
+        def flush():
+            nonlocal batch, samples
+            rows = []
+            if staged is not None and staged.meta:
+                self._flush_staged(staged, rows)
+            if batch:
+                self._flush(batch, rows)
+                batch = []
+            samples = 0
+            rows.sort(key=lambda r: r[0])
+            emit(rows)
+
+        with pool:
             while True:
                 while not exhausted and (ahead < self.batch_samples or not pending):
                     item = next(work_iter, None)
@@ -198,28 +306,34 @@ class repeatDetector(object):
                         exhausted = True
                         break
                     est = max(item[1].SEQ_LEN, 1) * self.SAMPLES_PER_BASE * len(item[3])
-                    pending.append((item, pool.submit(self._fetch, item), est))
+                    pending.append((item, submit(item), est))
                     ahead += est
                 if not pending:
                     break
                 item, fut, est = pending.popleft()
                 ahead -= est
-                _, raw = fut.result()
+                _, raw = result(fut)
                 if raw is None:
                     logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
                     continue
+                raw = np.asarray(raw)
+                stage_it = can_stage and raw.dtype == np.int16
+                if stage_it and staged is None:
+                    staged = _Staging(self.batch_samples + (8 << 20))
                 for name in item[3]:
-                    batch.append((item, raw, name))
+                    if stage_it:
+                        if not staged.fits(len(raw)):
+                            flush()                 # the I/O workers keep fetching the next batch meanwhile
+                            if not staged.fits(len(raw)):
+                                staged.grow(len(raw))
+                        staged.add(item, name, raw)
+                    else:
+                        batch.append((item, raw, name))
                     samples += len(raw)
                 if samples >= self.batch_samples:
-                    rows = []
-                    self._flush(batch, rows)   # the I/O threads keep fetching the next batch meanwhile
-                    emit(rows)
-                    batch, samples = [], 0
-        if batch:
-            rows = []
-            self._flush(batch, rows)
-            emit(rows)
+                    flush()
+        if batch or (staged is not None and staged.meta):
+            flush()
 
     def detect_records(self, work):
         """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""

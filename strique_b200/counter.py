@@ -118,23 +118,40 @@ class repeatCounter(object):
             return []
         tids = np.array([self._target_id(name, strand) for name, _, strand in items], dtype=np.int32)
         raw, off, kind = _lib.Context._pack_raw([np.asarray(sig) for _, sig, _ in items])
+        return self._detect_packed(tids, raw, off, kind, details)
+
+    def detect_packed(self, targets, raw, offsets, details=False):
+        """targets: [(target_name, strand)] per read; raw: ONE int16 (or float64) array holding the reads back to back
+        (e.g. a _lib.PinnedBuffer the fast5 signals were decoded into), offsets: [n + 1] sample offsets.  Same result
+        as detect_batch without the concatenation."""
+        if not targets:
+            return []
+        tids = np.array([self._target_id(name, strand) for name, strand in targets], dtype=np.int32)
+        raw = np.asarray(raw)
+        if raw.dtype not in (np.int16, np.float64):
+            raise ValueError('RepeatCounter: packed signals must be int16 or float64')
+        return self._detect_packed(tids, raw, np.ascontiguousarray(offsets, dtype=np.int64), 0 if raw.dtype == np.int16 else 1,
+                                   details)
+
+    def _detect_packed(self, tids, raw, off, kind, details):
         res, mod = self.context.detect_batch(self._detect_config(), raw, off, kind, tids)
+        # column-wise to Python objects: per-row access to a structured array costs ~10 us per read, as much as the
+        # GPU needs for the read
+        ran = res['hmm_ran'].astype(bool)
+        # the reference leaves n and p at the int 0 when the HMM stage is skipped or finds no path
+        counts = np.where(ran, res['count'], 0).tolist()
+        logp = res['log_p'].tolist()
+        cols = [res[f].tolist() for f in ('score_prefix', 'score_suffix', 'offset', 'ticks', 'mod_off', 'mod_len')]
+        patterns = None
+        if (res['mod_len'] >= 0).any():
+            patterns = mod.tobytes()
         out = []
-        for k in range(len(items)):
-            r = res[k]
-            if r['mod_len'] >= 0:
-                pattern = mod[r['mod_off']:r['mod_off'] + r['mod_len']].tobytes().decode('ascii')
-            else:
-                pattern = '-'
-            ran = bool(r['hmm_ran'])
-            # the reference leaves n and p at the int 0 when the HMM stage is skipped or finds no path
-            n = int(r['count']) if ran else 0
-            p = float(r['log_p']) if ran else 0
-            rec = (n, float(r['score_prefix']), float(r['score_suffix']), p, int(r['offset']), int(r['ticks']), pattern)
-            if details:
-                rec = DetectRecord(*rec, int(r['prefix_begin']), int(r['prefix_end']), int(r['suffix_begin']),
-                                   int(r['suffix_end']))
-            out.append(rec)
+        for k, (sp, ss, offset, ticks, mo, ml) in enumerate(zip(*cols)):
+            pattern = patterns[mo:mo + ml].decode('ascii') if ml >= 0 else '-'
+            out.append((counts[k], sp, ss, logp[k] if ran[k] else 0, offset, ticks, pattern))
+        if details:
+            extra = [res[f].tolist() for f in ('prefix_begin', 'prefix_end', 'suffix_begin', 'suffix_end')]
+            out = [DetectRecord(*rec, *e) for rec, e in zip(out, zip(*extra))]
         return out
 
     def detect(self, target_name, raw_signal, strand):

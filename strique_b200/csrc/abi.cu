@@ -27,6 +27,20 @@ strique_ctx::~strique_ctx() {
 
 extern "C" int strique_version(void) { return 200; }
 
+// Page-locked host memory for the batch staging buffers of the caller (strique_detect_batch then uploads at PCIe
+// speed instead of through the driver's bounce buffer).
+extern "C" void *strique_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void strique_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int strique_ctx_create(int device, strique_ctx **out) {
     if (!out) return STRIQUE_EINVAL;
     *out = nullptr;

@@ -42,3 +42,31 @@ def test_index_then_count_on_bundled_read(tmp_path):
     assert float(cols[6]) == pytest.approx(-119860.52066647023, rel=0.02)
     assert set(cols[9]) <= {'0', '1'} and abs(len(cols[9]) - int(cols[3])) <= 3
     assert len(lines) == 2
+
+
+def test_count_on_multi_read_fast5_files_with_worker_processes(tmp_path):
+    """N1 + N2 through the command line: 48 synthetic panel reads in multi-read fast5 files (deflate-chunked), decoded by
+    --t 4 worker PROCESSES into the pinned staging buffer, several GPU batches (STRIQUE_BATCH_SAMPLES), rows in input
+    order and equal to what repeatCounter.detect_batch gives for the same signals."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import make_fast5_dataset as mk
+    from strique_b200 import workload
+    from strique_b200.counter import repeatCounter
+    from strique_b200.pore_model import pore_model
+    model = os.path.join(ROOT, 'models', 'r9_4_450bps.model')
+    reads = workload.make_reads(pore_model(model), 48, seed=99, loci=workload.PANEL, n_lo=2, n_hi=150)
+    index_file, sam_file, ids = mk.build(str(tmp_path / 'ds'), reads, per_file=20, procs=2)
+    out = tmp_path / 'out.tsv'
+    env = dict(os.environ, STRIQUE_BATCH_SAMPLES=str(400000))
+    subprocess.run([sys.executable, SCRIPT, 'count', index_file, model, os.path.join(ROOT, 'configs', 'panel_config.tsv'),
+                    '--algn', sam_file, '--t', '4', '--out', str(out)], check=True, env=env)
+    rows = [l.split('\t') for l in out.read_text().strip().split('\n')[1:]]
+    assert [r[0] for r in rows] == ids
+    dt = repeatCounter(model)
+    for name in workload.PANEL:
+        dt.add_target(name, *workload.LOCI[name])
+    want = dt.detect_batch([(name, sig, strand) for name, sig, strand, _ in reads])
+    for r, (name, _, strand, _), w in zip(rows, reads, want):
+        assert r[1:3] == [name, strand]
+        assert r[3:] == [str(x) for x in w]
