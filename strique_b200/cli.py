@@ -108,7 +108,12 @@ def decode_sam(sam_line):
 
 
 # ---- fast5 decoding in worker PROCESSES (--t > 1): the HDF5 walk is Python and holds the GIL, only zlib does not --
+# Decoded signals come back through shared-memory slots, not through the result pipe (one parent process unpickling
+# 80 KB per read tops out near 200 MB/s, i.e. ~2.5 k reads/s): a task names a slot, the worker writes the signals of
+# its reads into it back to back and returns only their lengths.
 _worker_index = None
+_worker_slots = {}
+SLOT_SAMPLES = 8 << 20                        # int16 samples per slot (16 MB): a task of 16 reads of up to 500 k samples
 
 
 def _worker_init(index_file):
@@ -117,11 +122,48 @@ def _worker_init(index_file):
     _worker_index = fast5.fast5Index(index_file)
 
 
-def _worker_fetch(read_id):
-    try:
-        return _worker_index.get_raw(read_id), None
-    except Exception as e:  # noqa: BLE001 - a bad read must not stop the others (S.py:764-768)
-        return None, str(e)
+def _worker_fetch(read_ids, slot_name):
+    """-> (lengths: samples written into the slot per read, -1 failed, -2 returned in `spill` instead; spill: signals
+    that are not int16 or did not fit the slot; error messages)"""
+    from multiprocessing import shared_memory
+    shm = _worker_slots.get(slot_name)
+    if shm is None:
+        shm = _worker_slots[slot_name] = shared_memory.SharedMemory(name=slot_name)
+        try:    # the parent owns the segment; attaching must not make this process's resource tracker unlink it
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, 'shared_memory')
+        except Exception:  # noqa: BLE001
+            pass
+    dst = np.frombuffer(shm.buf, dtype=np.int16)
+    lens, spill, errs, pos = [], [], [], 0
+    for rid in read_ids:
+        try:
+            raw = np.asarray(_worker_index.get_raw(rid))
+        except Exception as e:  # noqa: BLE001 - a bad read must not stop the others (S.py:764-768)
+            lens.append(-1)
+            errs.append(str(e))
+            continue
+        if raw.dtype == np.int16 and pos + len(raw) <= len(dst):
+            dst[pos:pos + len(raw)] = raw
+            pos += len(raw)
+            lens.append(len(raw))
+        else:
+            lens.append(-2)
+            spill.append(raw)
+    return lens, spill, errs
+
+
+class _PoolCtx(object):
+    """`with` wrapper that also releases the shared-memory slots of the worker pool"""
+
+    def __init__(self, pool, close):
+        self.pool, self.close = pool, close
+
+    def __enter__(self):
+        return self.pool
+
+    def __exit__(self, *a):
+        return self.close(*a)
 
 
 class _Staging(object):
@@ -250,41 +292,76 @@ class repeatDetector(object):
         self._rows(st.meta, results, rows)
         st.reset()
 
+    FETCH_CHUNK = 16                           # reads per task of a worker process
+
     def _pool(self):
-        """--t worker processes decoding fast5 (each loads the index itself), or threads for --t 1 / a stub index /
-        STRIQUE_IO_THREADS=1.  -> (executor, submit(item) -> future of (item, raw or None))"""
+        """--t worker processes decoding fast5 (each loads the index itself; tasks of FETCH_CHUNK reads), or threads
+        for --t 1 / a stub index / STRIQUE_IO_THREADS=1.
+        -> (executor, submit(items) -> future, result(future) -> [(item, raw or None)], chunk size)"""
         index_file = getattr(self.f5, 'index_file', None)
         if self.io_threads > 1 and index_file and not os.environ.get('STRIQUE_IO_THREADS'):
             import multiprocessing as mp
+            from multiprocessing import shared_memory
             pool = ProcessPoolExecutor(self.io_threads, mp_context=mp.get_context('spawn'), initializer=_worker_init,
                                        initargs=(index_file,))
+            slots, free = [], deque()
 
-            def submit(item):
-                fut = pool.submit(_worker_fetch, item[1].QNAME)
-                fut.item = item
+            def submit(items):
+                if not free:
+                    shm = shared_memory.SharedMemory(create=True, size=SLOT_SAMPLES * 2)
+                    slots.append(shm)
+                    free.append(shm)
+                shm = free.popleft()
+                fut = pool.submit(_worker_fetch, [it[1].QNAME for it in items], shm.name)
+                fut.items, fut.shm = items, shm
                 return fut
 
             def result(fut):
-                raw, err = fut.result()
-                if err:
+                lens, spill, errs = fut.result()
+                for err in errs:
                     logger.log('Detector: {}'.format(err), 'warning')
-                return fut.item, raw
-            return pool, submit, result
+                src = np.frombuffer(fut.shm.buf, dtype=np.int16)
+                out, pos, k = [], 0, 0
+                for item, n in zip(fut.items, lens):
+                    if n == -1:
+                        out.append((item, None))
+                    elif n == -2:
+                        out.append((item, spill[k]))
+                        k += 1
+                    else:
+                        out.append((item, src[pos:pos + n]))      # a view: the caller copies it into its batch buffer
+                        pos += n
+                fut.release = lambda: free.append(fut.shm)
+                return out
+
+            orig_exit = pool.__exit__
+
+            def close_all(*a):
+                r = orig_exit(*a)
+                for shm in slots:
+                    try:
+                        shm.close()
+                        shm.unlink()
+                    except Exception:  # noqa: BLE001
+                        pass
+                return r
+            pool.__exit__ = close_all
+            return _PoolCtx(pool, close_all), submit, result, self.FETCH_CHUNK
         pool = ThreadPoolExecutor(self.io_threads)
-        return pool, (lambda item: pool.submit(self._fetch, item)), (lambda fut: fut.result())
+        return pool, (lambda items: pool.submit(self._fetch, items[0])), (lambda fut: [fut.result()]), 1
 
     def detect_stream(self, work_iter, emit):
         """work_iter: items of plan_iter() (possibly one rank's share); emit(rows) is called once per GPU batch with
         that batch's (input index, row tuple) list, in input order.  Fetches run ahead of the GPU on the I/O workers,
         at most one batch worth of (estimated) samples ahead -- fetched signals never pile up unbounded."""
-        pending = deque()                      # (item, future, estimated samples)
+        pending = deque()                      # (future of a chunk of items, estimated samples)
         ahead = 0
         batch, samples = [], 0
         staged = None                          # _Staging once the first int16 signal has arrived
         can_stage = hasattr(self.repeatCounter, 'detect_packed')
         work_iter = iter(work_iter)
         exhausted = False
-        pool, submit, result = self._pool()
+        pool, submit, result, chunk = self._pool()
 
         def flush():
             nonlocal batch, samples
@@ -301,37 +378,45 @@ class repeatDetector(object):
         with pool:
             while True:
                 while not exhausted and (ahead < self.batch_samples or not pending):
-                    item = next(work_iter, None)
-                    if item is None:
+                    items, est = [], 0
+                    for item in work_iter:
+                        items.append(item)
+                        est += max(item[1].SEQ_LEN, 1) * self.SAMPLES_PER_BASE * len(item[3])
+                        if len(items) >= chunk:
+                            break
+                    if not items:
                         exhausted = True
                         break
-                    est = max(item[1].SEQ_LEN, 1) * self.SAMPLES_PER_BASE * len(item[3])
-                    pending.append((item, submit(item), est))
+                    pending.append((submit(items), est))
                     ahead += est
                 if not pending:
                     break
-                item, fut, est = pending.popleft()
+                fut, est = pending.popleft()
                 ahead -= est
-                _, raw = result(fut)
-                if raw is None:
-                    logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
-                    continue
-                raw = np.asarray(raw)
-                stage_it = can_stage and raw.dtype == np.int16
-                if stage_it and staged is None:
-                    staged = _Staging(self.batch_samples + (8 << 20))
-                for name in item[3]:
-                    if stage_it:
-                        if not staged.fits(len(raw)):
-                            flush()                 # the I/O workers keep fetching the next batch meanwhile
+                for item, raw in result(fut):
+                    if raw is None:
+                        logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
+                        continue
+                    raw = np.asarray(raw)
+                    stage_it = can_stage and raw.dtype == np.int16
+                    if stage_it and staged is None:
+                        staged = _Staging(self.batch_samples + (8 << 20))
+                    if not stage_it and raw.base is not None:
+                        raw = raw.copy()                # (a view into a worker's slot, which is about to be reused)
+                    for name in item[3]:
+                        if stage_it:
                             if not staged.fits(len(raw)):
-                                staged.grow(len(raw))
-                        staged.add(item, name, raw)
-                    else:
-                        batch.append((item, raw, name))
-                    samples += len(raw)
-                if samples >= self.batch_samples:
-                    flush()
+                                flush()                 # the I/O workers keep fetching the next batch meanwhile
+                                if not staged.fits(len(raw)):
+                                    staged.grow(len(raw))
+                            staged.add(item, name, raw)
+                        else:
+                            batch.append((item, raw, name))
+                        samples += len(raw)
+                    if samples >= self.batch_samples:
+                        flush()
+                if hasattr(fut, 'release'):
+                    fut.release()                       # the slot's signals have been copied out
         if batch or (staged is not None and staged.meta):
             flush()
 
