@@ -129,11 +129,7 @@ def _worker_fetch(read_ids, slot_name):
     shm = _worker_slots.get(slot_name)
     if shm is None:
         shm = _worker_slots[slot_name] = shared_memory.SharedMemory(name=slot_name)
-        try:    # the parent owns the segment; attaching must not make this process's resource tracker unlink it
-            from multiprocessing import resource_tracker
-            resource_tracker.unregister(shm._name, 'shared_memory')
-        except Exception:  # noqa: BLE001
-            pass
+
     dst = np.frombuffer(shm.buf, dtype=np.int16)
     lens, spill, errs, pos = [], [], [], 0
     for rid in read_ids:
@@ -340,8 +336,11 @@ class repeatDetector(object):
                 r = orig_exit(*a)
                 for shm in slots:
                     try:
-                        shm.close()
                         shm.unlink()
+                    except Exception:  # noqa: BLE001
+                        pass
+                    try:
+                        shm.close()                 # (refuses while numpy views of the slot are alive; harmless)
                     except Exception:  # noqa: BLE001
                         pass
                 return r
