@@ -257,6 +257,11 @@ int strique_detect_batch(strique_ctx *ctx, const strique_detect_config *cfg, int
 
 int64_t strique_last_mod_bytes(const strique_ctx *ctx);
 
+/* 1 when a flank of n_levels k-mer levels with `samples` samples per level fits the alignment kernels (at most
+ * 2048 flank samples = levels x samples; up to 319 levels at samples = 6, the reference's default, run the fast kernels).  The reference aligns
+ * flanks of any length (src/align_raw.h:117-158); longer ones are refused when the target is defined. */
+int strique_align_supported(int n_levels, int samples);
+
 /* Page-locked host memory for the caller's batch staging buffers (raw of strique_detect_batch with STRIQUE_HOST):
  * the read-batching driver writes decoded fast5 signals straight into it (the reference hands numpy arrays from
  * h5py to its workers, STRique_lib/fast5Index.py:76-84).  NULL when the allocation fails. */

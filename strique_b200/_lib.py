@@ -128,6 +128,8 @@ def load():
     lib.strique_last_viterbi_declined.argtypes = [c_void_p]
     lib.strique_set_viterbi_exact.restype = c_int
     lib.strique_set_viterbi_exact.argtypes = [c_void_p, c_int]
+    lib.strique_align_supported.restype = c_int
+    lib.strique_align_supported.argtypes = [c_int, c_int]
     lib.strique_host_alloc.restype = c_void_p
     lib.strique_host_alloc.argtypes = [ctypes.c_size_t]
     lib.strique_host_free.restype = None

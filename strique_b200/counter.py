@@ -93,6 +93,12 @@ class repeatCounter(object):
         suffix_ext = suffix.upper()
         suffix = suffix[:50].upper()
         repeat = repeat.upper()
+        # the reference aligns flanks of any length; the kernels here hold a flank in the registers of one warp
+        for flank in (prefix_ext, suffix_ext):
+            levels = len(flank) - self.pm.kmer + 1
+            if levels < 1 or not _lib.load().strique_align_supported(levels, int(self.samples)):
+                raise ValueError("RepeatCounter: flank of {} nt x {} samples does not fit the alignment kernels "
+                                 "(at most 2048 flank samples = (nt - k + 1) x samples).".format(len(flank), self.samples))
         rc = self.__reverse_complement__
         tc_plus, id_plus = self._make_classifier(repeat, prefix, suffix, prefix_ext, suffix_ext)
         tc_minus, id_minus = self._make_classifier(rc(repeat), rc(suffix), rc(prefix), rc(suffix_ext), rc(prefix_ext))

@@ -27,6 +27,13 @@ strique_ctx::~strique_ctx() {
 
 extern "C" int strique_version(void) { return 200; }
 
+// 1 when a flank of n_levels k-mer levels, `samples` samples each, fits an alignment kernel (callers check when a
+// target is defined, not when the first batch fails)
+extern "C" int strique_align_supported(int n_levels, int samples) {
+    int K = 0, S = 0;
+    return n_levels > 0 && samples > 0 && strique::align_pick_kernel(n_levels, samples, &K, &S) ? 1 : 0;
+}
+
 // Page-locked host memory for the batch staging buffers of the caller (strique_detect_batch then uploads at PCIe
 // speed instead of through the driver's bounce buffer).
 extern "C" void *strique_host_alloc(size_t bytes) {
@@ -145,7 +152,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         if (nlev <= 0 || N <= 0) FAIL(ctx, STRIQUE_EINVAL, "empty signal or flank (the reference returns FLT_MIN; handle it in the caller)");
         if (N >= (1ll << 30)) FAIL(ctx, STRIQUE_EUNSUPPORTED, "signal longer than 2^30 samples");
         int K, S;
-        if (!align_pick_kernel(nlev, in.samples, &K, &S)) FAIL(ctx, STRIQUE_EUNSUPPORTED, "flank too long for the alignment kernels (max 1920 samples at samples=6, 1024 otherwise)");
+        if (!align_pick_kernel(nlev, in.samples, &K, &S)) FAIL(ctx, STRIQUE_EUNSUPPORTED, "flank too long for the alignment kernels (at most 2048 flank samples = levels x samples per level)");
         tK[t] = K;
         tS[t] = S;
         maxRows = std::max(maxRows, 32 * K * S);

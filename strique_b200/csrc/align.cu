@@ -900,7 +900,7 @@ int launch_trace_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, i
 // (K levels per lane, S samples per level) instantiations.  S = 6 is the reference's flank
 // sampling (scripts/STRique.py:507-513 'samples'); S = 1 serves arbitrary flank vectors.
 #define STRIQUE_ALIGN_INSTANCES(X) \
-    X(2, 6) X(3, 6) X(4, 6) X(5, 6) X(6, 6) X(7, 6) X(8, 6) X(9, 6) X(10, 6) X(4, 1) X(8, 1) X(16, 1) X(32, 1)
+    X(2, 6) X(3, 6) X(4, 6) X(5, 6) X(6, 6) X(7, 6) X(8, 6) X(9, 6) X(10, 6) X(4, 1) X(8, 1) X(16, 1) X(32, 1) X(64, 1)
 
 // linear gap costs: the scan may use LinSweep (see there for the exactness argument)
 bool align_params_linear(const strique_align_params &p) {
@@ -917,8 +917,8 @@ bool align_pick_kernel(int nlev, int samples, int *K, int *S) {
             if (k * 32 > nlev) { *K = k; *S = 6; return true; }
     }
     const int rows = nlev * samples;
-    const int ks[4] = {4, 8, 16, 32};
-    for (int i = 0; i < 4; ++i)
+    const int ks[5] = {4, 8, 16, 32, 64};
+    for (int i = 0; i < 5; ++i)
         if (ks[i] * 32 >= rows) { *K = ks[i]; *S = 1; return true; }
     return false;
 }

@@ -53,6 +53,19 @@ def test_no_cpu_fallback_without_a_device(lib):
         dt.add_target('c9orf72', 'GGCCCC', C9_PREFIX, C9_SUFFIX)   # registering the HMMs needs the device
 
 
+def test_flank_shapes_the_alignment_kernels_hold(lib):
+    """host-only query used by repeatCounter.add_target: the limits the header states"""
+    assert lib.strique_align_supported(145, 6) == 1          # the reference's default: 150 nt flanks, 6 samples per level
+    assert lib.strique_align_supported(341, 6) == 1 and lib.strique_align_supported(342, 6) == 0      # 2048 flank samples
+    assert lib.strique_align_supported(256, 8) == 1 and lib.strique_align_supported(257, 8) == 0
+    assert lib.strique_align_supported(0, 6) == 0
+    from strique_b200.counter import repeatCounter
+    from .conftest import C9_SUFFIX
+    dt = repeatCounter(os.path.join(ROOT, 'models', 'r9_4_450bps.model'))
+    with pytest.raises(ValueError, match='does not fit the alignment kernels'):
+        dt.add_target('long', 'GGCCCC', 'ACGT' * 100, C9_SUFFIX)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, 'strique_b200')
     for dirpath, _, files in os.walk(pkg):

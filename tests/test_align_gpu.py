@@ -151,3 +151,33 @@ def test_linear_gap_scan_equals_affine_scan_and_oracle(ctx, monkeypatch):
     slow = ctx.align_batch(*args)
     monkeypatch.delenv('STRIQUE_NO_LINEAR_SCAN', raising=False)
     assert fast.tobytes() == slow.tobytes()
+
+
+def test_long_flanks_and_other_samples_per_level(ctx):
+    """Flank shapes beyond the default 145 levels x 6 samples: 8 samples per level (the one-row-per-register
+    kernels, up to 2048 flank samples) and 300 levels x 6.  Bit-exact against the oracle."""
+    c = rp.CAligner()
+    ps = ac.PARAM_SETS[0]
+    _set(c, ps)
+    al = sa.align_raw(ctx)
+    _set(al, ps)
+    rng = np.random.default_rng(31)
+    cs = []
+    for nlev, s in ((200, 8), (255, 8), (300, 6), (319, 6), (335, 6), (150, 7)):
+        lev = np.round(rng.uniform(60, 120, nlev))
+        b = np.repeat(lev, s)
+        a = np.concatenate([np.round(rng.uniform(60, 120, 400)), np.repeat(lev, rng.integers(s - 1, s + 3, nlev)),
+                            np.round(rng.uniform(60, 120, 400))])
+        cs.append((a, b))
+    got = al.align_overlap_batch(cs)
+    for (a, b), (score, a_idx, b_idx) in zip(cs, got):
+        s0, a0, b0 = c.align_overlap(a, b)
+        assert np.float32(score) == np.float32(s0)
+        assert np.array_equal(a_idx, a0) and np.array_equal(b_idx, b0)
+
+
+def test_flank_beyond_the_kernels_is_refused_when_the_target_is_defined(ctx, model_file):
+    from strique_b200 import counter
+    rd = counter.repeatCounter(model_file, context=ctx)
+    with pytest.raises(ValueError, match='does not fit the alignment kernels'):
+        rd.add_target('long', 'GGCCCC', 'ACGT' * 100, C9_SUFFIX)
