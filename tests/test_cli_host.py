@@ -158,3 +158,43 @@ def test_failing_batch_is_retried_read_by_read(tmp_path):
     out = tmp_path / 'o.tsv'
     assert cli.run_count(rd, iter([_sam(i) for i in range(6)]), str(out)) == 5   # read003 is dropped, the rest survive
     assert calls[0] == 6 and calls.count(1) == 6
+
+
+def test_tsv_consumers_of_the_reference_parse_our_rows(tmp_path):
+    """the reference's downstream tools work off the unchanged TSV.  The two parse expressions are
+    restated from scripts/fast5Masker.py:55-60 (typed record, then mask[offset:offset+ticks]) and
+    scripts/STRique.py:972-990 (`plot`: nine positional fields); rows come from the golden sets through our writer,
+    including a mod string and a degenerate all-zero row."""
+    import json
+    from collections import namedtuple
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'pipeline_golden.json')))['sets']
+    rows = []
+    for name in ('c2_small', 'c3_mod'):
+        for k, r in enumerate(golden[name]['rows'][:20]):
+            rows.append(('%s-%d' % (name, k), r['target'], r['strand'], r['count'], r['score_prefix'], r['score_suffix'],
+                         r['log_p'], r['offset'], r['ticks'], r['mod']))
+    rows.append(('none', 'c9orf72', '+', 0, 0.0, 0.0, 0, 0, 0, '-'))
+    out = tmp_path / 'counts.tsv'
+    ow = cli.outputWriter(str(out))
+    ow.write_line(rows)
+    ow.close()
+    # fast5Masker
+    Record = namedtuple('STRique_record', ['ID', 'target', 'strand', 'count', 'score_prefix', 'score_suffix', 'log_p', 'offset', 'ticks', 'mod'])
+    with open(out) as fp:
+        fields = (row.strip().split('\t') for row in fp if row and not row.startswith('ID'))
+        records = [Record(*row[:3], int(row[3]), *[float(x) for x in row[4:7]], int(row[7]), int(row[8]), row[9]) for row in fields]
+    assert len(records) == len(rows)
+    assert any(set(r.mod) <= set('01') and len(r.mod) > 10 for r in records if r.mod != '-')
+    for rec, row in zip(records, rows):
+        assert (rec.ID, rec.count, rec.offset, rec.ticks, rec.mod) == (row[0], row[3], row[7], row[8], row[9])
+        assert rec.log_p == float(row[6]) and rec.score_prefix == row[4]
+        raw = np.arange(rec.offset + rec.ticks + 100, dtype=np.int16)
+        mask = np.ones(raw.shape, dtype=bool)
+        mask[rec.offset:rec.offset + rec.ticks] = False
+        assert len(raw[mask]) == len(raw) - rec.ticks
+    # plot
+    with open(out) as fp:
+        for line in fp:
+            if not line.startswith('ID'):
+                ID, target, strand, count, score_prefix, score_suffix, _, offset, ticks = line.strip().split('\t')[:9]
+                assert int(offset) >= 0 and int(ticks) >= 0 and float(score_prefix) >= 0.0 and float(score_suffix) >= 0.0
