@@ -174,7 +174,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
            &d_tS = ctx->buf("al.tS"), &d_order = ctx->buf("al.order"), &d_ckoff = ctx->buf("al.ckoff"),
            &d_lut = ctx->buf("al.lut"), &d_ckpt = ctx->buf("al.ckpt"), &d_trace = ctx->buf("al.trace"),
            &d_rows = ctx->buf("al.rows"), &d_res = ctx->buf("al.res"), &d_queue = ctx->buf("al.queue"),
-           &d_fix = ctx->buf("al.fix");
+           &d_fix = ctx->buf("al.fix"), &d_patch = ctx->buf("al.patch");
     // chunk tasks so LUT + checkpoints stay within a device-memory budget
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, ctx_mem_info(ctx, &free_b, &total_b));
@@ -186,10 +186,12 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
     CUDA_TRY(ctx, cudaMemcpyAsync(d_col0.as<float>(), col0.data(), col0.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     TRY(d_trace.ensure(ctx, (size_t)trace_warps * ALIGN_CKPT * 32 * maxW * sizeof(uint32_t)));
     TRY(d_queue.ensure(ctx, 64));
-    TRY(d_fix.ensure(ctx, (size_t)(fix_cap + 1) * sizeof(unsigned long long)));
+    TRY(d_fix.ensure(ctx, (size_t)(2 * fix_cap + 1) * sizeof(unsigned long long)));
+    TRY(d_patch.ensure(ctx, (size_t)2 * fix_cap * sizeof(unsigned long long)));
 
     std::vector<strique_align_result> res_chunk;
-    std::vector<unsigned long long> fix_host(fix_cap + 1);
+    std::vector<unsigned long long> fix_host(2 * fix_cap + 1), patch_host;
+    const unsigned long long fix_head = 255;        // entries read back together with the count
     int64_t cells_total = 0;
     float scan_ms_total = 0.f;
     int t0 = 0;
@@ -247,29 +249,36 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         TRY(align_launch_build_lut(ctx, b, d_tK.as<int32_t>(), d_tS.as<int32_t>(), n));
         stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TABLE + 1);
         // ---- patch table entries too close to an fp32 rounding midpoint with libm's pow -------
-        CUDA_TRY(ctx, cudaMemcpyAsync(fix_host.data(), d_fix.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(fix_host.data(), d_fix.p, (1 + 2 * fix_head) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        unsigned long long nfix = fix_host[0];
+        const unsigned long long nfix = fix_host[0];
         if (nfix > (unsigned long long)fix_cap) FAIL(ctx, STRIQUE_EUNSUPPORTED, "too many borderline score-table entries");
+        if (nfix > fix_head)
+            CUDA_TRY(ctx, cudaMemcpy(fix_host.data() + 1 + 2 * fix_head, (char *)d_fix.p + (1 + 2 * fix_head) * 8, (nfix - fix_head) * 16, cudaMemcpyDeviceToHost));
         if (nfix) {
-            CUDA_TRY(ctx, cudaMemcpy(fix_host.data() + 1, (char *)d_fix.p + 8, nfix * 8, cudaMemcpyDeviceToHost));
+            patch_host.resize(2 * nfix);
             for (unsigned long long k = 0; k < nfix; ++k) {
-                const int t = (int)(fix_host[1 + k] >> 40);
-                const int64_t e = (int64_t)(fix_host[1 + k] & ((1ull << 40) - 1));
-                const int row_len = 32 * tK[t0 + t];
+                const int t = (int)(fix_host[1 + 2 * k] >> 40);
+                const int64_t e = (int64_t)(fix_host[1 + 2 * k] & ((1ull << 40) - 1));
+                const int Kt = tK[t0 + t], row_len = 32 * Kt;
                 const int c = (int)(e / row_len), u = (int)(e % row_len);
-                const int sg = task_signal[t0 + t], f = task_flank[t0 + t];
                 float h, v;
-                CUDA_TRY(ctx, cudaMemcpy(&h, in.code_values + (size_t)sg * in.n_code_values + c, 4, cudaMemcpyDeviceToHost));
-                CUDA_TRY(ctx, cudaMemcpy(&v, in.flank_levels + in.flank_off_host[f] + (u * tS[t0 + t]) / in.samples, 4, cudaMemcpyDeviceToHost));
+                const uint32_t hb = (uint32_t)(fix_host[2 + 2 * k] >> 32), vb = (uint32_t)fix_host[2 + 2 * k];
+                memcpy(&h, &hb, 4);
+                memcpy(&v, &vb, 4);
                 const float d = h > v ? h - v : v - h;
                 volatile float fx = (float)pow((double)d, 1.2);
-                volatile float s = params.dist_offset - fx;
-                const float out = s > params.dist_min ? s : params.dist_min;
-                const int Kt = tK[t0 + t];                                   // stored [u % K][u / K] inside the code row
-                const int64_t pos = (int64_t)c * row_len + (u % Kt) * 32 + u / Kt;
-                CUDA_TRY(ctx, cudaMemcpy(b.lut + (size_t)t * lut_task_stride + pos, &out, 4, cudaMemcpyHostToDevice));
+                volatile float sc = params.dist_offset - fx;
+                const float out = sc > params.dist_min ? sc : params.dist_min;
+                uint32_t ob;
+                memcpy(&ob, &out, 4);
+                const int64_t pos = (int64_t)c * row_len + (u % Kt) * 32 + u / Kt;       // stored [u % K][u / K] inside the code row
+                patch_host[2 * k] = (unsigned long long)((int64_t)t * lut_task_stride + pos);
+                patch_host[2 * k + 1] = ob;
             }
+            // (pageable source: the copy returns once the host buffer has been staged, so patch_host may be reused)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_patch.p, patch_host.data(), nfix * 16, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(align_launch_patch_lut(ctx, b.lut, d_patch.as<unsigned long long>(), (int)nfix));
         }
         // ---- groups by kernel instantiation, longest signal first -----------------------------
         std::vector<int32_t> order(n);

@@ -25,12 +25,12 @@ __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? l
 // there pow(d, 1.2) exceeds off - min by far more than any rounding in the chain, so off - fx <= min.  With the
 // reference's parameters (off 16, min 0) that is every |v - y| > 10.08, about three quarters of the table.
 __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, const int32_t *task_K, const int32_t *task_S,
-                                                              int n_tasks, const float far) {
-    // One CTA = 32 codes of one task; a warp takes one flank level at a time with one code per lane.  The code
+                                                              int n_tasks, const float far, const int tile_codes) {
+    // One CTA = tile_codes (32; 16 for the 64-rows-per-lane kernels, whose rows would not fit) codes of one task; a warp takes one flank level at a time with one code per lane.  The code
     // values rise with the code, so the lanes near a level form a contiguous run and most warps see only far
     // pairs and skip pow altogether.  The tile goes through shared memory so that the table rows (code-major)
     // are still written coalesced.
-    extern __shared__ float tile[];                  // [32][row_len + 1]
+    extern __shared__ float tile[];                  // [tile_codes][row_len + 1]
     const int t = blockIdx.y;
     if (t >= n_tasks) return;
     const int K = task_K[t], S = task_S[t];
@@ -43,12 +43,13 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
     const float *lev = b.flank_levels + b.flank_off[f];
     float *lut = b.lut + (size_t)t * b.lut_task_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int c0 = blockIdx.x * 32; c0 < b.n_code_values; c0 += gridDim.x * 32) {
+    for (int c0 = blockIdx.x * tile_codes; c0 < b.n_code_values; c0 += gridDim.x * tile_codes) {
         const int c = c0 + lane;
-        const float h = c < b.n_code_values ? vals[c] : 0.f;
+        const bool mine = lane < tile_codes && c < b.n_code_values;
+        const float h = mine ? vals[c] : 0.f;
         for (int u = warp; u < row_len; u += n_warps) {
             float out = 0.f;
-            if (u < nlev && c < b.n_code_values) {
+            if (u < nlev && mine) {
                 const float v = lev[(u * S) / b.samples];
                 const float d = h > v ? h - v : v - h;
                 if (d > far) {
@@ -60,17 +61,19 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
                     const long long low = (long long)(bits & 0x1FFFFFFFull) - 0x10000000ll;
                     if ((low < 0 ? -low : low) <= 16 && b.lut_fix != nullptr) {
                         unsigned long long k = atomicAdd(b.lut_fix, 1ull);
-                        if (k < (unsigned long long)b.lut_fix_cap)
-                            b.lut_fix[1 + k] = ((unsigned long long)t << 40) | (unsigned long long)(c * row_len + u);
+                        if (k < (unsigned long long)b.lut_fix_cap) {       // where, and the two operands (one read-back)
+                            b.lut_fix[1 + 2 * k] = ((unsigned long long)t << 40) | (unsigned long long)(c * row_len + u);
+                            b.lut_fix[2 + 2 * k] = ((unsigned long long)__float_as_uint(h) << 32) | __float_as_uint(v);
+                        }
                     }
                     const float s = b.p.dist_offset - fx;
                     out = s > b.p.dist_min ? s : b.p.dist_min;
                 }
             }
-            tile[lane * pitch + u] = out;
+            if (lane < tile_codes) tile[lane * pitch + u] = out;
         }
         __syncthreads();
-        const int n_codes = min(32, b.n_code_values - c0);
+        const int n_codes = min(tile_codes, b.n_code_values - c0);
         // storage order inside a code row: [k][lane] for level u = lane * K + k, so that the scan's K loads per
         // column are one 128-byte line each
         for (int e = threadIdx.x; e < n_codes * row_len; e += blockDim.x) {
@@ -947,10 +950,25 @@ int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t 
     float far = INFINITY;
     const double span = (double)b.p.dist_offset - (double)b.p.dist_min;
     if (span > 0.0 && span < 1e30) far = (float)(pow(span * (1.0 + 1e-5), 1.0 / 1.2) * (1.0 + 1e-6));
-    const size_t smem = (size_t)32 * (b.lut_row + 1) * sizeof(float);     // lut_row = 32 * Kmax of the batch
+    const int tile_codes = b.lut_row > 1024 ? 16 : 32;                    // lut_row = 32 * Kmax of the batch
+    const size_t smem = (size_t)tile_codes * (b.lut_row + 1) * sizeof(float);
     if (smem > 48 * 1024)
         CUDA_TRY(ctx, cudaFuncSetAttribute(align_build_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    align_build_lut_kernel<<<grid, 256, smem, ctx->stream>>>(b, task_K, task_S, n_tasks, far);
+    align_build_lut_kernel<<<grid, 256, smem, ctx->stream>>>(b, task_K, task_S, n_tasks, far, tile_codes);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return STRIQUE_OK;
+}
+
+__global__ void align_patch_lut_kernel(float *lut, const unsigned long long *patch, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lut[patch[2 * i]] = __uint_as_float((unsigned)patch[2 * i + 1]);
+}
+
+// patch = n pairs {element index into lut, fp32 bits}
+int align_launch_patch_lut(strique_ctx *ctx, float *lut, const unsigned long long *patch, int n) {
+    if (n == 0) return STRIQUE_OK;
+    align_patch_lut_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(lut, patch, n);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return STRIQUE_OK;

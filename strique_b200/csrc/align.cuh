@@ -87,6 +87,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
                      const int32_t *task_post, strique_align_result *results_host, int32_t *rows_out_host,
                      int64_t rows_out_stride, strique_align_result *results_dev_out);
 
+int align_launch_patch_lut(strique_ctx *ctx, float *lut, const unsigned long long *patch, int n);
 int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t *task_K, const int32_t *task_S,
                            int n_tasks);
 int align_launch_scan(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g);

@@ -38,7 +38,7 @@ def main():
     commit = subprocess.run(['git', '-C', ROOT, 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
     data[key] = {'bytes_per_unit': traffic / per_launch, 'unit': 'DP cell' if rk == 'align_scan' else 'Viterbi column',
                  'dram_bytes_of_the_captured_launch': traffic, 'units_of_the_captured_launch': per_launch,
-                 'kernel': vals[hdr.index('Kernel Name')][:80], 'source': 'profiles/' + os.path.basename(rep).replace('.ncu-rep', '.txt'),
+                 'kernel': vals[hdr.index('Kernel Name')][:80], 'source': 'profiles/ncu_' + os.path.basename(rep).replace('.ncu-rep', '.txt'),
                  'commit': commit}
     json.dump(data, open(path, 'w'), indent=1)
     print(key, data[key])
