@@ -281,7 +281,7 @@ def reference_main(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def cli_e2e(args, n_reads):
+def cli_e2e(args, n_reads, ctx=None):
     """`scripts/STRique.py count` as a user runs it: index of multi-read fast5 files + SAM on disk -> TSV, wall clock of
     the whole process (interpreter start, CUDA context, HMM build, fast5 decode in --t worker processes, GPU batches,
     row writing).  The data set is written first (untimed).  -> dict for the JSON line"""
@@ -302,6 +302,7 @@ def cli_e2e(args, n_reads):
                '--out', os.path.join(tmp, 'out.tsv')]
         if args.mod:
             cmd += ['--mod_model', MOD_MODEL]
+        inflate = inflate_bench(ctx, index_file, ['synth-%08d' % k for k in range(min(n_reads, 8192))]) if ctx is not None else None
         # start-up alone (empty SAM): interpreter, CUDA context, HMMs of the panel
         empty = os.path.join(tmp, 'empty.sam')
         open(empty, 'w').write('@HD\tVN:1.6\n')
@@ -311,6 +312,12 @@ def cli_e2e(args, n_reads):
         t0 = time.time()
         subprocess.run(cmd, check=True, capture_output=True)
         wall = time.time() - t0
+        # the same with zlib on the worker processes (what the reference's h5py does)
+        t0 = time.time()
+        subprocess.run([os.path.join(tmp, 'out_host.tsv') if c == os.path.join(tmp, 'out.tsv') else c for c in cmd], check=True, capture_output=True,
+                       env=dict(os.environ, STRIQUE_HOST_INFLATE='1'))
+        wall_host = time.time() - t0
+        same = open(os.path.join(tmp, 'out_host.tsv')).read() == open(os.path.join(tmp, 'out.tsv')).read()
         rows = open(os.path.join(tmp, 'out.tsv')).read().strip().split('\n')[1:]
         truth = {('synth-%08d' % k): r[3] for k, r in enumerate(reads)}
         exact = sum(1 for r in rows if int(r.split('\t')[3]) == truth[r.split('\t')[0]])
@@ -318,12 +325,53 @@ def cli_e2e(args, n_reads):
         return {'value': n_reads / wall, 'unit': 'reads/s', 'reads': n_reads, 'wall_s': wall, 'startup_s': t_start,
                 'value_after_startup': n_reads / max(wall - t_start, 1e-9), 'io_workers': min(cores, 32),
                 'rows': len(rows), 'count_exact': exact, 'fast5_mb': fast5_mb, 'dataset_build_s': t_make,
+                'inflate': 'GPU (strique_inflate_batch)', 'inflate_kernel': inflate,
+                'host_inflate': {'value': n_reads / wall_host, 'wall_s': wall_host,
+                                 'value_after_startup': n_reads / max(wall_host - t_start, 1e-9), 'same_rows': same},
                 'what': 'scripts/STRique.py count <index> <model> <panel_config> --algn <sam> --t <workers> --out <tsv> on '
                         'multi-read fast5 files (deflate), wall clock of the process'}
     except Exception as e:  # noqa: BLE001 - the hot-path numbers above must survive a failure here
         return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def inflate_bench(ctx, index_file, ids):
+    """strique_inflate_batch alone on the stored Signal chunks of `ids`: compressed bytes in page-locked host memory
+    -> samples in HBM (upload + kernel + status read-back, as the CLI calls it), and with the compressed bytes already
+    on the device (kernel + status only).  Wall clock around the synchronous entry, best of 3 after a warm-up."""
+    import torch
+    from strique_b200 import _lib, fast5
+    f5 = fast5.fast5Index(index_file)
+    recs, parts, pos, base = [], [], 0, 0
+    for rid in ids:
+        st = f5.get_stored(rid)
+        if st[0] != 'chunks':
+            return None
+        _, buf, n, clen, chunks = st
+        for off0, a, cs in chunks:
+            recs.append((pos, (base + off0) * 2, cs, min(clen, n - off0) * 2, clen * 2, 0))
+            parts.append(np.frombuffer(buf, dtype=np.uint8, count=cs, offset=a))
+            pos += cs
+        base += n
+    chunks = np.array(recs, dtype=_lib.INFLATE_CHUNK_DTYPE)
+    pinned = _lib.PinnedBuffer(pos + 16, np.uint8)
+    pinned.array[:pos] = np.concatenate(parts)
+    dev_comp = torch.from_numpy(pinned.array[:pos].copy()).cuda()
+    out = {}
+    for name, comp, space in (('from_pinned_host', pinned.array, _lib.HOST), ('from_device', dev_comp.data_ptr(), _lib.DEVICE)):
+        best = None
+        for k in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, status = ctx.inflate_batch(comp, pos, chunks, base * 2, memspace=space)
+            dt = time.perf_counter() - t0
+            if k and (best is None or dt < best):
+                best = dt
+        out[name] = {'ms': best * 1e3, 'samples_GBps': base * 2 / best / 1e9, 'reads_per_s': len(ids) / best}
+    out.update({'reads': len(ids), 'chunks': len(recs), 'compressed_mb': pos / 1e6, 'samples_mb': base * 2 / 1e6,
+                'failed_chunks': int(np.count_nonzero(status))})
+    return out
 
 
 def init_distributed(local_rank, world):
@@ -542,7 +590,7 @@ def main():
                        if (int(cpu_res[k][0]), int(cpu_res[k][4]), int(cpu_res[k][5])) !=
                        (int(res['count'][k]) if res['hmm_ran'][k] else 0, int(res['offset'][k]), int(res['ticks'][k])))
             if args.cli_reads > 0:
-                line['cli_e2e'] = cli_e2e(args, args.cli_reads)
+                line['cli_e2e'] = cli_e2e(args, args.cli_reads, ctx)
             line['cpu_baseline'] = {'value': n_sample / wall, 'unit': 'reads/s', 'cores': min(cores, n_sample),
                                     'kind': cpu_kind(),
                                     'sample': 'first %d reads of the step, workers pull reads longest first, %.1f s wall'

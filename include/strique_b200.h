@@ -268,6 +268,29 @@ int strique_align_supported(int n_levels, int samples);
 void *strique_host_alloc(size_t bytes);
 void strique_host_free(void *p);
 
+/* ---- fast5 Signal chunks -> raw samples on the device -------------------------------------------------------
+ * Replaces h5py's read of a deflate-filtered Signal dataset (STRique_lib/fast5Index.py:76-84: `fp[...][()]`, zlib
+ * inflate of every chunk on the CPU).  HDF5 stores each chunk as an independent zlib stream; the caller locates the
+ * chunks of a batch of reads (B-tree walk, no decompression), packs the stored bytes into `comp` (host or device)
+ * and describes where each chunk's samples belong in the batch's raw-sample buffer.  One call inflates all of them
+ * into a device buffer owned by the context (valid until the next call), which is then handed to
+ * strique_detect_batch / strique_condition_batch as `raw` with STRIQUE_DEVICE.
+ *   status_host[i] (written for every chunk): 0 ok, 1 not a zlib stream, 2 bad block header, 3 bad Huffman code,
+ *   4 more output than `full`, 5 match before the start of the chunk, 6 stream longer than src_len, 7 Adler-32
+ *   mismatch, 8 fewer than `keep` bytes.  The call itself succeeds when some chunks fail; the samples of such a
+ *   chunk are undefined and the caller drops the read. */
+typedef struct strique_inflate_chunk {
+    int64_t src_off;      /* byte offset of the chunk's zlib stream in comp                                       */
+    int64_t dst_off;      /* byte offset in the output of the chunk's first sample                                */
+    int32_t src_len;      /* stored size of the chunk                                                             */
+    int32_t keep;         /* bytes of the chunk that belong to the dataset (HDF5 pads the last chunk)             */
+    int32_t full;         /* chunk size in bytes: the most the stream may produce                                 */
+    int32_t reserved;
+} strique_inflate_chunk;
+int strique_inflate_batch(strique_ctx *ctx, const void *comp, int64_t comp_bytes, int comp_memspace,
+                          const strique_inflate_chunk *chunks /* host */, int n_chunks, int64_t out_bytes,
+                          int32_t *status_host, void **out_dev);
+
 /* device time of the stages of the last strique_detect_batch call (ms) */
 #define STRIQUE_STAGE_CONDITION 0
 #define STRIQUE_STAGE_ALIGN_TABLE 1

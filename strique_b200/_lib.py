@@ -128,6 +128,9 @@ def load():
     lib.strique_last_viterbi_declined.argtypes = [c_void_p]
     lib.strique_set_viterbi_exact.restype = c_int
     lib.strique_set_viterbi_exact.argtypes = [c_void_p, c_int]
+    lib.strique_inflate_batch.restype = c_int
+    lib.strique_inflate_batch.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p,
+                                          ctypes.POINTER(c_void_p)]
     lib.strique_align_supported.restype = c_int
     lib.strique_align_supported.argtypes = [c_int, c_int]
     lib.strique_host_alloc.restype = c_void_p
@@ -332,6 +335,16 @@ class Context:
             break
         return res, mod
 
+    def inflate_batch(self, comp, comp_bytes, chunks, out_bytes, memspace=HOST):
+        """fast5 Signal chunks (zlib streams packed in `comp`) -> samples in a device buffer of the context.
+        chunks: INFLATE_CHUNK_DTYPE array.  -> (device pointer, per-chunk status)"""
+        chunks = np.ascontiguousarray(chunks, dtype=INFLATE_CHUNK_DTYPE)
+        status = np.zeros(max(len(chunks), 1), dtype=np.int32)
+        out = ctypes.c_void_p()
+        self.check(self.lib.strique_inflate_batch(self.handle, _ptr(comp), int(comp_bytes), memspace, _ptr(chunks), len(chunks),
+                                                  int(out_bytes), _ptr(status), ctypes.byref(out)), 'strique_inflate_batch')
+        return int(out.value or 0), status[:len(chunks)]
+
     def stage_ms(self):
         return {name: float(self.lib.strique_last_stage_ms(self.handle, i)) for i, name in enumerate(STAGES)}
 
@@ -348,6 +361,13 @@ class Context:
     def last_viterbi_fixed(self):
         """(sequences decoded in fixed point, sequences handed on to the float64 kernel) of the last call"""
         return (int(self.lib.strique_last_viterbi_fixed(self.handle)), int(self.lib.strique_last_viterbi_declined(self.handle)))
+
+
+INFLATE_CHUNK_DTYPE = np.dtype([('src_off', np.int64), ('dst_off', np.int64), ('src_len', np.int32), ('keep', np.int32),
+                                ('full', np.int32), ('reserved', np.int32)])
+INFLATE_STATUS = {1: 'not a zlib stream', 2: 'bad block header', 3: 'bad Huffman code', 4: 'more output than the chunk holds',
+                  5: 'match before the start of the chunk', 6: 'stream longer than its stored size', 7: 'Adler-32 mismatch',
+                  8: 'chunk shorter than the dataset needs'}
 
 
 class PinnedBuffer(object):

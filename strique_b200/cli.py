@@ -149,6 +149,67 @@ def _worker_fetch(read_ids, slot_name):
     return lens, spill, errs
 
 
+class StoredRead(object):
+    """A read whose Signal chunks are still deflate-compressed (fast5.stored_raw_signal): samples, samples per chunk,
+    [(first sample, stored bytes)] and the stored bytes of all chunks back to back (uint8 view)."""
+    __slots__ = ('n', 'clen', 'chunks', 'data')
+
+    def __init__(self, n, clen, chunks, data):
+        self.n, self.clen, self.chunks, self.data = n, clen, chunks, data
+
+
+def _stored_chunks_into(st, dst, pos):
+    """copy the stored bytes of the chunks of one read (st = fast5.stored_raw_signal result) to dst[pos:]
+    -> (record for the parent, bytes written) or None when they do not fit"""
+    _, buf, n, clen, chunks = st
+    total = sum(cs for _, _, cs in chunks)
+    if pos + total > len(dst):
+        return None
+    p = pos
+    for _, a, cs in chunks:
+        dst[p:p + cs] = np.frombuffer(buf, dtype=np.uint8, count=cs, offset=a)
+        p += cs
+    return ('c', n, clen, [(off0, cs) for off0, _, cs in chunks]), total
+
+
+def _worker_fetch_stored(read_ids, slot_name):
+    """Like _worker_fetch, but deflate-compressed reads are NOT inflated: their stored chunk bytes go into the slot
+    and the GPU inflates them (strique_inflate_batch).  -> (records, spill, errors); a record is None (failed),
+    ('c', samples, samples per chunk, [(first sample, stored bytes)]) with the bytes in the slot, ('r', samples) with
+    int16 samples in the slot (a dataset stored some other way), or ('s',) with the decoded signal in `spill`."""
+    from multiprocessing import shared_memory
+    shm = _worker_slots.get(slot_name)
+    if shm is None:
+        shm = _worker_slots[slot_name] = shared_memory.SharedMemory(name=slot_name)
+    dst = np.frombuffer(shm.buf, dtype=np.uint8)
+    recs, spill, errs, pos = [], [], [], 0
+    for rid in read_ids:
+        try:
+            st = _worker_index.get_stored(rid)
+            if st[0] == 'chunks':
+                put = _stored_chunks_into(st, dst, pos)
+                if put is not None:
+                    recs.append(put[0])
+                    pos += put[1]
+                    continue
+                raw = np.asarray(_worker_index.get_raw(rid))
+            else:
+                raw = np.asarray(st[1])
+        except Exception as e:  # noqa: BLE001 - a bad read must not stop the others (S.py:764-768)
+            recs.append(None)
+            errs.append(str(e))
+            continue
+        pos += pos & 1
+        if raw.dtype == np.int16 and pos + 2 * len(raw) <= len(dst):
+            dst[pos:pos + 2 * len(raw)] = raw.view(np.uint8)
+            pos += 2 * len(raw)
+            recs.append(('r', len(raw)))
+        else:
+            recs.append(('s',))
+            spill.append(raw)
+    return recs, spill, errs
+
+
 class _PoolCtx(object):
     """`with` wrapper that also releases the shared-memory slots of the worker pool"""
 
@@ -190,6 +251,38 @@ class _Staging(object):
         self.meta.append((item, name))
 
 
+class _StoredStaging(object):
+    """Reads of one GPU batch as fast5 stores them: the zlib streams of their Signal chunks back to back in ONE
+    page-locked byte buffer + one strique_inflate_chunk record per chunk.  The samples only ever exist on the device."""
+
+    def __init__(self, capacity_bytes):
+        from . import _lib
+        self._lib = _lib
+        self.buf = _lib.PinnedBuffer(capacity_bytes, np.uint8)
+        self.reset()
+
+    def reset(self):
+        self.meta, self.offsets, self.pos, self.chunks, self.chunk_read = [], [0], 0, [], []
+
+    def fits(self, nbytes):
+        return self.pos + nbytes <= len(self.buf.array)
+
+    def grow(self, nbytes):
+        self.buf = self._lib.PinnedBuffer(nbytes + (nbytes >> 2), np.uint8)
+
+    def add(self, item, name, sr):
+        nb = len(sr.data)
+        self.buf.array[self.pos:self.pos + nb] = sr.data
+        base, src = self.offsets[-1], self.pos
+        for off0, cs in sr.chunks:
+            self.chunks.append((src, (base + off0) * 2, cs, min(sr.clen, sr.n - off0) * 2, sr.clen * 2, 0))
+            self.chunk_read.append(len(self.meta))
+            src += cs
+        self.pos += nb
+        self.offsets.append(base + sr.n)
+        self.meta.append((item, name))
+
+
 class repeatDetector(object):
     """Multi-locus repeat detection over SAM records (scripts/STRique.py:624-705), batched."""
 
@@ -208,6 +301,10 @@ class repeatDetector(object):
         self.io_threads = max(int(io_threads), 1)
         # samples per GPU batch: ~8 k reads of 45 k samples (0.8 GB of int16 on the host and on the device)
         self.batch_samples = int(batch_samples or os.environ.get('STRIQUE_BATCH_SAMPLES', 384 << 20))
+        # deflate-compressed Signal chunks are inflated on the GPU (strique_inflate_batch); STRIQUE_HOST_INFLATE=1:
+        # by zlib on the I/O workers, like the reference's h5py
+        self.gpu_inflate = (hasattr(self.repeatCounter, 'detect_deflated') and hasattr(self.f5, 'get_stored')
+                            and not os.environ.get('STRIQUE_HOST_INFLATE'))
 
     def __init_hmm__(self):
         for target_name, (chrom, begin, end, repeat, prefix, suffix) in self.repeat_config.items():
@@ -288,13 +385,55 @@ class repeatDetector(object):
         self._rows(st.meta, results, rows)
         st.reset()
 
+    def _flush_stored(self, st, rows):
+        """st: _StoredStaging -- compressed chunks to the device, inflated there"""
+        from . import _lib
+        targets = [(name, item[2]) for item, name in st.meta]
+        chunks = np.array(st.chunks, dtype=_lib.INFLATE_CHUNK_DTYPE)
+        try:
+            results, status = self.repeatCounter.detect_deflated(targets, st.buf.array, st.pos, chunks, st.offsets)
+            results = list(results)
+            for c in np.nonzero(status)[0]:
+                k = st.chunk_read[c]
+                if results[k] is not None:
+                    logger.log('Detector: damaged Signal chunk in read {} ({})'.format(
+                        st.meta[k][0][1].QNAME, _lib.INFLATE_STATUS.get(int(status[c]), status[c])), 'warning')
+                    results[k] = None
+        except Exception as e:  # noqa: BLE001 - isolate the failing read (decoded on the host this time)
+            logger.log('Detector: batch of {} reads failed ({}); retrying read by read'.format(len(targets), e), 'warning')
+            results = []
+            for (item, name) in st.meta:
+                try:
+                    results.append(self.repeatCounter.detect(name, self.f5.get_raw(item[1].QNAME), item[2]))
+                except Exception as e2:  # noqa: BLE001
+                    logger.log('Detector: read failed: {}'.format(e2), 'warning')
+                    results.append(None)
+        self._rows(st.meta, results, rows)
+        st.reset()
+
+    def _fetch_stored(self, item):
+        """thread-pool twin of _worker_fetch_stored"""
+        try:
+            st = self.f5.get_stored(item[1].QNAME)
+            if st[0] != 'chunks':
+                return item, np.asarray(st[1])
+            total = sum(cs for _, _, cs in st[4])
+            data = np.empty(total, np.uint8)
+            rec, _ = _stored_chunks_into(st, data, 0)
+            return item, StoredRead(rec[1], rec[2], rec[3], data)
+        except Exception as e:  # noqa: BLE001
+            logger.log('Detector: {}'.format(e), 'warning')
+            return item, None
+
     FETCH_CHUNK = 16                           # reads per task of a worker process
 
     def _pool(self):
-        """--t worker processes decoding fast5 (each loads the index itself; tasks of FETCH_CHUNK reads), or threads
-        for --t 1 / a stub index / STRIQUE_IO_THREADS=1.
-        -> (executor, submit(items) -> future, result(future) -> [(item, raw or None)], chunk size)"""
+        """--t worker processes reading fast5 (each loads the index itself; tasks of FETCH_CHUNK reads), or threads
+        for --t 1 / a stub index / STRIQUE_IO_THREADS=1.  With `gpu_inflate` the workers only locate and copy the
+        stored chunks of deflate-compressed reads; otherwise they decode them.
+        -> (executor, submit(items) -> future, result(future) -> [(item, int16 array | StoredRead | None)], chunk size)"""
         index_file = getattr(self.f5, 'index_file', None)
+        stored = getattr(self, 'gpu_inflate', False)
         if self.io_threads > 1 and index_file and not os.environ.get('STRIQUE_IO_THREADS'):
             import multiprocessing as mp
             from multiprocessing import shared_memory
@@ -308,25 +447,42 @@ class repeatDetector(object):
                     slots.append(shm)
                     free.append(shm)
                 shm = free.popleft()
-                fut = pool.submit(_worker_fetch, [it[1].QNAME for it in items], shm.name)
+                fut = pool.submit(_worker_fetch_stored if stored else _worker_fetch, [it[1].QNAME for it in items], shm.name)
                 fut.items, fut.shm = items, shm
                 return fut
 
             def result(fut):
-                lens, spill, errs = fut.result()
+                recs, spill, errs = fut.result()
                 for err in errs:
                     logger.log('Detector: {}'.format(err), 'warning')
-                src = np.frombuffer(fut.shm.buf, dtype=np.int16)
                 out, pos, k = [], 0, 0
-                for item, n in zip(fut.items, lens):
-                    if n == -1:
-                        out.append((item, None))
-                    elif n == -2:
-                        out.append((item, spill[k]))
-                        k += 1
-                    else:
-                        out.append((item, src[pos:pos + n]))      # a view: the caller copies it into its batch buffer
-                        pos += n
+                if stored:
+                    src = np.frombuffer(fut.shm.buf, dtype=np.uint8)
+                    for item, rec in zip(fut.items, recs):
+                        if rec is None:
+                            out.append((item, None))
+                        elif rec[0] == 'c':
+                            nb = sum(cs for _, cs in rec[3])
+                            out.append((item, StoredRead(rec[1], rec[2], rec[3], src[pos:pos + nb])))
+                            pos += nb
+                        elif rec[0] == 'r':
+                            pos += pos & 1
+                            out.append((item, src[pos:pos + 2 * rec[1]].view(np.int16)))
+                            pos += 2 * rec[1]
+                        else:
+                            out.append((item, spill[k]))
+                            k += 1
+                else:
+                    src = np.frombuffer(fut.shm.buf, dtype=np.int16)
+                    for item, n in zip(fut.items, recs):
+                        if n == -1:
+                            out.append((item, None))
+                        elif n == -2:
+                            out.append((item, spill[k]))
+                            k += 1
+                        else:
+                            out.append((item, src[pos:pos + n]))      # a view: the caller copies it into its batch buffer
+                            pos += n
                 fut.release = lambda: free.append(fut.shm)
                 return out
 
@@ -347,7 +503,8 @@ class repeatDetector(object):
             pool.__exit__ = close_all
             return _PoolCtx(pool, close_all), submit, result, self.FETCH_CHUNK
         pool = ThreadPoolExecutor(self.io_threads)
-        return pool, (lambda items: pool.submit(self._fetch, items[0])), (lambda fut: [fut.result()]), 1
+        fetch = self._fetch_stored if stored else self._fetch
+        return pool, (lambda items: pool.submit(fetch, items[0])), (lambda fut: [fut.result()]), 1
 
     def detect_stream(self, work_iter, emit):
         """work_iter: items of plan_iter() (possibly one rank's share); emit(rows) is called once per GPU batch with
@@ -357,6 +514,7 @@ class repeatDetector(object):
         ahead = 0
         batch, samples = [], 0
         staged = None                          # _Staging once the first int16 signal has arrived
+        stored = None                          # _StoredStaging once the first still-compressed read has arrived
         can_stage = hasattr(self.repeatCounter, 'detect_packed')
         work_iter = iter(work_iter)
         exhausted = False
@@ -365,6 +523,8 @@ class repeatDetector(object):
         def flush():
             nonlocal batch, samples
             rows = []
+            if stored is not None and stored.meta:
+                self._flush_stored(stored, rows)
             if staged is not None and staged.meta:
                 self._flush_staged(staged, rows)
             if batch:
@@ -396,6 +556,19 @@ class repeatDetector(object):
                     if raw is None:
                         logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
                         continue
+                    if isinstance(raw, StoredRead):
+                        if stored is None:
+                            stored = _StoredStaging(self.batch_samples * 2 + (16 << 20))
+                        for name in item[3]:
+                            if not stored.fits(len(raw.data)):
+                                flush()             # the I/O workers keep fetching the next batch meanwhile
+                                if not stored.fits(len(raw.data)):
+                                    stored.grow(len(raw.data))
+                            stored.add(item, name, raw)
+                            samples += raw.n
+                        if samples >= self.batch_samples:
+                            flush()
+                        continue
                     raw = np.asarray(raw)
                     stage_it = can_stage and raw.dtype == np.int16
                     if stage_it and staged is None:
@@ -416,7 +589,7 @@ class repeatDetector(object):
                         flush()
                 if hasattr(fut, 'release'):
                     fut.release()                       # the slot's signals have been copied out
-        if batch or (staged is not None and staged.meta):
+        if batch or (staged is not None and staged.meta) or (stored is not None and stored.meta):
             flush()
 
     def detect_records(self, work):

@@ -139,8 +139,20 @@ class repeatCounter(object):
         return self._detect_packed(tids, raw, np.ascontiguousarray(offsets, dtype=np.int64), 0 if raw.dtype == np.int16 else 1,
                                    details)
 
-    def _detect_packed(self, tids, raw, off, kind, details):
-        res, mod = self.context.detect_batch(self._detect_config(), raw, off, kind, tids)
+    def detect_deflated(self, targets, comp, comp_bytes, chunks, offsets, details=False):
+        """Reads still compressed as fast5 stores them: `comp` holds the zlib streams of the Signal chunks (e.g. a
+        uint8 _lib.PinnedBuffer), `chunks` (_lib.INFLATE_CHUNK_DTYPE) says where each chunk's samples belong in the
+        batch, offsets: [n + 1] sample offsets of the reads.  The chunks are inflated on the device
+        (strique_inflate_batch) and never exist on the host.  -> (rows like detect_packed, per-chunk status)"""
+        if not targets:
+            return [], np.zeros(0, np.int32)
+        tids = np.array([self._target_id(name, strand) for name, strand in targets], dtype=np.int32)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        dev, status = self.context.inflate_batch(comp, comp_bytes, chunks, int(off[-1]) * 2)
+        return self._detect_packed(tids, dev, off, 0, details, memspace=_lib.DEVICE), status
+
+    def _detect_packed(self, tids, raw, off, kind, details, memspace=_lib.HOST):
+        res, mod = self.context.detect_batch(self._detect_config(), raw, off, kind, tids, memspace=memspace)
         # column-wise to Python objects: per-row access to a structured array costs ~10 us per read, as much as the
         # GPU needs for the read
         ran = res['hmm_ran'].astype(bool)

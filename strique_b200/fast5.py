@@ -239,7 +239,8 @@ class _MiniHDF5:
         return visit(self.resolve(raw_group_path))
 
     # -- datasets -------------------------------------------------------------------------------
-    def read_dataset(self, addr):
+    def _dataset_header(self, addr):
+        """-> (shape, dtype, layout message, [(filter id, client data)])"""
         shape = dtype = layout = None
         filters = []
         for mtype, _, d in self._messages(addr):
@@ -275,6 +276,47 @@ class _MiniHDF5:
                     filters.append((fid, cd))
         if shape is None or dtype is None or layout is None:
             raise HDF5Error('incomplete dataset header')
+        return shape, dtype, layout, filters
+
+    def stored_chunks(self, addr):
+        """The chunks of a 1-D little-endian int16 dataset whose only filter is deflate, WITHOUT decompressing them:
+        -> (samples, samples per chunk, [(first sample, byte offset in the file, stored bytes)]) for
+        strique_inflate_batch, or None when the dataset is stored any other way (read_dataset decodes those)."""
+        shape, dtype, layout, filters = self._dataset_header(addr)
+        if layout[1] != 2 or len(shape) != 1 or dtype != np.dtype('<i2') or [f for f, _ in filters] != [1]:
+            return None
+        rank = layout[2]
+        if rank != 2:
+            return None
+        btree = self._u_b(layout, 3, 8)
+        clen = self._u_b(layout, 11, 4)
+        chunks = []
+        if btree != _UNDEF and not self._list_chunks(btree, rank, chunks):
+            return None
+        return int(shape[0]), int(clen), chunks
+
+    def _list_chunks(self, node_addr, rank, out):
+        n = node_addr + self.base
+        if self.buf[n:n + 4] != b'TREE':
+            raise HDF5Error('bad chunk B-tree node')
+        level, used = self.buf[n + 5], self._u(n + 6, 2)
+        keysize = 8 + 8 * rank
+        p = n + 24
+        for k in range(used):
+            kp = p + k * (keysize + 8)
+            csize, fmask = self._u(kp, 4), self._u(kp + 4, 4)
+            child = self._u(kp + keysize, 8)
+            if level > 0:
+                if not self._list_chunks(child, rank, out):
+                    return False
+                continue
+            if fmask:                             # a chunk the filter was skipped for
+                return False
+            out.append((self._u(kp + 8, 8), child + self.base, csize))
+        return True
+
+    def read_dataset(self, addr):
+        shape, dtype, layout, filters = self._dataset_header(addr)
         n = int(np.prod(shape)) if shape else 1
         cls = layout[1]
         if cls == 0:     # compact
@@ -376,6 +418,23 @@ def read_raw_signal(f5_file, offset=''):
     return f.read_dataset(addr)
 
 
+def stored_raw_signal(f5_file, offset=''):
+    """Like read_raw_signal, but deflate-compressed Signal datasets stay compressed:
+    -> ('chunks', file buffer, samples, samples per chunk, [(first sample, byte offset, stored bytes)]) or
+       ('raw', int16 array) for every other storage (and when h5py does the reading)."""
+    if _h5py is not None:  # pragma: no cover - depends on the environment
+        return ('raw', read_raw_signal(f5_file, offset))
+    raw_group = '/'.join([x for x in (offset, 'Raw') if x])
+    f = _open(f5_file)
+    addr = f.find_signal(raw_group)
+    if addr is None:
+        raise HDF5Error('no Signal dataset below ' + raw_group)
+    stored = f.stored_chunks(addr)
+    if stored is None:
+        return ('raw', f.read_dataset(addr))
+    return ('chunks', f.buf) + stored
+
+
 def read_id_of(f5_file, offset=''):
     """`read_id` attribute of the group holding the Signal dataset (fast5Index.py:62-74)."""
     raw_group = '/'.join([x for x in (offset, 'Raw') if x])
@@ -459,6 +518,20 @@ class fast5Index(object):
         try:
             return read_raw_signal(f5_file, offset)
         except Exception as e:  # noqa: BLE001 - same catch-all as the reference (the cause is appended)
+            raise RuntimeError('[ERROR] Could not retrieve {ID} from file {file}. ({why})'.format(ID=ID, file=f5_file, why=e))
+
+    def get_stored(self, ID):
+        """get_raw for callers that inflate on the GPU: see stored_raw_signal.  Tar-archived reads come decoded."""
+        assert self.index_dict
+        if ID not in self.index_dict:
+            raise RuntimeError('[Error] Read {ID} not found in {index}.'.format(ID=ID, index=self.index_file))
+        target = re.split(r'(\.fast5|\.tar)\/', self.index_dict[ID])
+        if len(target) > 1 and target[1] != '.fast5':
+            return ('raw', self.get_raw(ID))
+        f5_file = os.path.join(self.index_dir, target[0] + ('.fast5' if len(target) > 1 else ''))
+        try:
+            return stored_raw_signal(f5_file, target[2] if len(target) > 1 else '')
+        except Exception as e:  # noqa: BLE001 - same catch-all as get_raw
             raise RuntimeError('[ERROR] Could not retrieve {ID} from file {file}. ({why})'.format(ID=ID, file=f5_file, why=e))
 
     def get_raw(self, ID):

@@ -70,3 +70,11 @@ def test_count_on_multi_read_fast5_files_with_worker_processes(tmp_path):
     for r, (name, _, strand, _), w in zip(rows, reads, want):
         assert r[1:3] == [name, strand]
         assert r[3:] == [str(x) for x in w]
+    # the run above inflated the Signal chunks on the GPU (strique_inflate_batch); zlib on the workers and the
+    # single-threaded default (--t 1) must give the same file
+    out2, out3 = tmp_path / 'out_host_inflate.tsv', tmp_path / 'out_t1.tsv'
+    subprocess.run([sys.executable, SCRIPT, 'count', index_file, model, os.path.join(ROOT, 'configs', 'panel_config.tsv'),
+                    '--algn', sam_file, '--t', '4', '--out', str(out2)], check=True, env=dict(env, STRIQUE_HOST_INFLATE='1'))
+    subprocess.run([sys.executable, SCRIPT, 'count', index_file, model, os.path.join(ROOT, 'configs', 'panel_config.tsv'),
+                    '--algn', sam_file, '--out', str(out3)], check=True, env=env)
+    assert out2.read_text() == out.read_text() == out3.read_text()

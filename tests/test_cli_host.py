@@ -198,3 +198,67 @@ def test_tsv_consumers_of_the_reference_parse_our_rows(tmp_path):
             if not line.startswith('ID'):
                 ID, target, strand, count, score_prefix, score_suffix, _, offset, ticks = line.strip().split('\t')[:9]
                 assert int(offset) >= 0 and int(ticks) >= 0 and float(score_prefix) >= 0.0 and float(score_suffix) >= 0.0
+
+
+@pytest.mark.parametrize('workers', [1, 2])
+def test_stored_reads_reach_the_counter_as_chunk_records(tmp_path, monkeypatch, workers):
+    """The GPU-inflate path of `count` without a GPU: reads of deflate-chunked multi-read fast5 files travel as
+    stored chunk bytes + strique_inflate_chunk records (worker threads for --t 1, worker processes otherwise); a stub
+    counter inflates the records with zlib and must recover exactly the signals get_raw decodes.  A contiguous
+    (uncompressed) file in the same run takes the decoded path."""
+    import zlib
+    from collections import defaultdict
+    from strique_b200 import _lib
+    from . import hdf5_writer as hw
+
+    class FakePinned(object):
+        def __init__(self, n, dtype=np.int16):
+            self.array = np.zeros(int(n), dtype)
+    monkeypatch.setattr(_lib, 'PinnedBuffer', FakePinned)
+    rng = np.random.default_rng(8)
+    sigs = {'read%03d' % i: rng.integers(200, 900, int(rng.integers(3000, 40000))).astype(np.int16) for i in range(40)}
+    ids = sorted(sigs)
+    hw.multi_read_fast5(str(tmp_path / 'a.fast5'), [(i, sigs[i]) for i in ids[:25]], chunk=8192, deflate=True)
+    hw.multi_read_fast5(str(tmp_path / 'b.fast5'), [(i, sigs[i]) for i in ids[25:35]], chunk=1000, deflate=True)
+    hw.multi_read_fast5(str(tmp_path / 'c.fast5'), [(i, sigs[i]) for i in ids[35:]])                 # contiguous
+    index = tmp_path / 'reads.fofn'
+    index.write_text(''.join('%s.fast5/read_%s\t%s\n' % ('a' if k < 25 else ('b' if k < 35 else 'c'), i, i)
+                             for k, i in enumerate(ids)))
+    seen = {}
+
+    class Counter(object):
+        targets = {}
+
+        def add_target(self, name, *a):
+            self.targets[name] = a
+
+        def detect_deflated(self, targets, comp, comp_bytes, chunks, offsets):
+            comp = np.asarray(comp)[:comp_bytes]
+            out = np.zeros(int(offsets[-1]), np.int16).view(np.uint8)
+            assert chunks.dtype == _lib.INFLATE_CHUNK_DTYPE
+            for c in chunks:
+                data = zlib.decompress(comp[c['src_off']:c['src_off'] + c['src_len']].tobytes())
+                assert len(data) == c['full'] and c['keep'] <= c['full']
+                out[c['dst_off']:c['dst_off'] + c['keep']] = np.frombuffer(data, np.uint8)[:c['keep']]
+            sam = out.view(np.int16)
+            for k in range(len(targets)):
+                seen[('stored', len(seen))] = sam[offsets[k]:offsets[k + 1]].copy()
+            return [(1, 1.0, 1.0, -1.0, 1, 1, '-')] * len(targets), np.zeros(len(chunks), np.int32)
+
+        def detect_packed(self, targets, raw, offsets):
+            for k in range(len(targets)):
+                seen[('packed', len(seen))] = np.array(raw[offsets[k]:offsets[k + 1]])
+            return [(1, 1.0, 1.0, -1.0, 1, 1, '-')] * len(targets)
+
+    rd = cli.repeatDetector.__new__(cli.repeatDetector)
+    rd.repeatCounter, rd.f5 = Counter(), fast5.fast5Index(str(index))
+    rd.repeatLoci, rd.repeat_config, rd.is_init = defaultdict(list), cli.parse_config(CONFIG_TSV)['repeat'], False
+    rd.io_threads, rd.batch_samples, rd.gpu_inflate = workers, 300000, True
+    out = tmp_path / 'o.tsv'
+    lines = ['\t'.join([i, '0', 'chr9', '27573000', '60', '1000M', '*', '0', '0', 'A' * 100, '*']) + '\n' for i in ids]
+    assert cli.run_count(rd, iter(lines), str(out)) == 40
+    assert [l.split('\t')[0] for l in out.read_text().strip().split('\n')[1:]] == ids
+    kinds = [k for k, _ in seen]
+    assert kinds.count('stored') == 35 and kinds.count('packed') == 5
+    got = sorted((a.tobytes() for a in seen.values()))
+    assert got == sorted(sigs[i].tobytes() for i in ids)
