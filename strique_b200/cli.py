@@ -210,19 +210,6 @@ def _worker_fetch_stored(read_ids, slot_name):
     return recs, spill, errs
 
 
-class _PoolCtx(object):
-    """`with` wrapper that also releases the shared-memory slots of the worker pool"""
-
-    def __init__(self, pool, close):
-        self.pool, self.close = pool, close
-
-    def __enter__(self):
-        return self.pool
-
-    def __exit__(self, *a):
-        return self.close(*a)
-
-
 class _Staging(object):
     """Reads of one GPU batch back to back in ONE page-locked int16 buffer: decoded signals are copied in as they
     arrive and the batch goes to strique_detect_batch without another concatenation, at pinned-memory PCIe speed."""
@@ -292,13 +279,15 @@ class repeatDetector(object):
     def __init__(self, repeat_config, model_file, fast5_index_file, mod_model_file=None, align_config=None,
                  HMM_config=None, device=0, io_threads=1, batch_samples=None, counter=None):
         from .counter import repeatCounter
+        self.f5 = fast5.fast5Index(fast5_index_file)
+        self.io_threads = max(int(io_threads), 1)
+        self._io = None
+        self._get_pool()                       # worker processes start (and load the index) while the CUDA context comes up
         self.repeatCounter = counter or repeatCounter(model_file, mod_model_file=mod_model_file,
                                                       align_config=align_config, HMM_config=HMM_config, device=device)
         self.repeatLoci = defaultdict(list)
         self.repeat_config = repeat_config
         self.is_init = False
-        self.f5 = fast5.fast5Index(fast5_index_file)
-        self.io_threads = max(int(io_threads), 1)
         # samples per GPU batch: ~8 k reads of 45 k samples (0.8 GB of int16 on the host and on the device)
         self.batch_samples = int(batch_samples or os.environ.get('STRIQUE_BATCH_SAMPLES', 384 << 20))
         # deflate-compressed Signal chunks are inflated on the GPU (strique_inflate_batch); STRIQUE_HOST_INFLATE=1:
@@ -427,18 +416,20 @@ class repeatDetector(object):
 
     FETCH_CHUNK = 16                           # reads per task of a worker process
 
-    def _pool(self):
+    def _get_pool(self):
         """--t worker processes reading fast5 (each loads the index itself; tasks of FETCH_CHUNK reads), or threads
-        for --t 1 / a stub index / STRIQUE_IO_THREADS=1.  With `gpu_inflate` the workers only locate and copy the
-        stored chunks of deflate-compressed reads; otherwise they decode them.
-        -> (executor, submit(items) -> future, result(future) -> [(item, int16 array | StoredRead | None)], chunk size)"""
+        for --t 1 / a stub index / STRIQUE_IO_THREADS=1; created once and kept until close().  With `gpu_inflate` the
+        workers only locate and copy the stored chunks of deflate-compressed reads; otherwise they decode them.
+        -> (submit(items) -> future, result(future) -> [(item, int16 array | StoredRead | None)], chunk size)"""
+        if getattr(self, '_io', None) is not None:
+            return self._io[1:]
         index_file = getattr(self.f5, 'index_file', None)
-        stored = getattr(self, 'gpu_inflate', False)
         if self.io_threads > 1 and index_file and not os.environ.get('STRIQUE_IO_THREADS'):
             import multiprocessing as mp
             from multiprocessing import shared_memory
             pool = ProcessPoolExecutor(self.io_threads, mp_context=mp.get_context('spawn'), initializer=_worker_init,
                                        initargs=(index_file,))
+            pool.submit(int)                   # (spawn starts every worker at the first submit)
             slots, free = [], deque()
 
             def submit(items):
@@ -447,8 +438,9 @@ class repeatDetector(object):
                     slots.append(shm)
                     free.append(shm)
                 shm = free.popleft()
+                stored = getattr(self, 'gpu_inflate', False)
                 fut = pool.submit(_worker_fetch_stored if stored else _worker_fetch, [it[1].QNAME for it in items], shm.name)
-                fut.items, fut.shm = items, shm
+                fut.items, fut.shm, fut.stored = items, shm, stored
                 return fut
 
             def result(fut):
@@ -456,7 +448,7 @@ class repeatDetector(object):
                 for err in errs:
                     logger.log('Detector: {}'.format(err), 'warning')
                 out, pos, k = [], 0, 0
-                if stored:
+                if fut.stored:
                     src = np.frombuffer(fut.shm.buf, dtype=np.uint8)
                     for item, rec in zip(fut.items, recs):
                         if rec is None:
@@ -486,10 +478,8 @@ class repeatDetector(object):
                 fut.release = lambda: free.append(fut.shm)
                 return out
 
-            orig_exit = pool.__exit__
-
-            def close_all(*a):
-                r = orig_exit(*a)
+            def close_all():
+                pool.shutdown(wait=True, cancel_futures=True)
                 for shm in slots:
                     try:
                         shm.unlink()
@@ -499,42 +489,82 @@ class repeatDetector(object):
                         shm.close()                 # (refuses while numpy views of the slot are alive; harmless)
                     except Exception:  # noqa: BLE001
                         pass
-                return r
-            pool.__exit__ = close_all
-            return _PoolCtx(pool, close_all), submit, result, self.FETCH_CHUNK
+            self._io = (close_all, submit, result, self.FETCH_CHUNK)
+            return self._io[1:]
         pool = ThreadPoolExecutor(self.io_threads)
-        fetch = self._fetch_stored if stored else self._fetch
-        return pool, (lambda items: pool.submit(fetch, items[0])), (lambda fut: [fut.result()]), 1
+
+        def submit_one(items):
+            return pool.submit(self._fetch_stored if getattr(self, 'gpu_inflate', False) else self._fetch, items[0])
+        self._io = ((lambda: pool.shutdown(wait=True, cancel_futures=True)), submit_one, (lambda fut: [fut.result()]), 1)
+        return self._io[1:]
+
+    def close(self):
+        """stop the I/O workers and release their shared-memory slots"""
+        io, self._io = getattr(self, '_io', None), None
+        if io is not None:
+            io[0]()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def detect_stream(self, work_iter, emit):
         """work_iter: items of plan_iter() (possibly one rank's share); emit(rows) is called once per GPU batch with
-        that batch's (input index, row tuple) list, in input order.  Fetches run ahead of the GPU on the I/O workers,
-        at most one batch worth of (estimated) samples ahead -- fetched signals never pile up unbounded."""
+        that batch's (input index, row tuple) list, in input order.  Three things overlap: the I/O workers fetch at
+        most one batch worth of (estimated) samples ahead -- fetched signals never pile up unbounded; this thread
+        copies what they return into the staging buffers of batch k + 1; a GPU thread runs batch k (two sets of
+        staging buffers, at most one batch in flight)."""
         pending = deque()                      # (future of a chunk of items, estimated samples)
         ahead = 0
-        batch, samples = [], 0
-        staged = None                          # _Staging once the first int16 signal has arrived
-        stored = None                          # _StoredStaging once the first still-compressed read has arrived
+        samples = 0
         can_stage = hasattr(self.repeatCounter, 'detect_packed')
         work_iter = iter(work_iter)
         exhausted = False
-        pool, submit, result, chunk = self._pool()
+        submit, result, chunk = self._get_pool()
+
+        class Buffers(object):                 # staging of one GPU batch
+            def __init__(self):
+                self.staged = None             # _Staging once the first int16 signal has arrived
+                self.stored = None             # _StoredStaging once the first still-compressed read has arrived
+                self.batch = []                # the generic path
+
+            def any(self):
+                return bool(self.batch or (self.staged is not None and self.staged.meta)
+                            or (self.stored is not None and self.stored.meta))
+
+        sets = [Buffers(), Buffers()]
+        cur = 0
+        gpu = ThreadPoolExecutor(1)
+        in_flight = None                       # future of the batch on the GPU
+
+        def run(b):
+            rows = []
+            if b.stored is not None and b.stored.meta:
+                self._flush_stored(b.stored, rows)
+            if b.staged is not None and b.staged.meta:
+                self._flush_staged(b.staged, rows)
+            if b.batch:
+                self._flush(b.batch, rows)
+                b.batch = []
+            rows.sort(key=lambda r: r[0])
+            return rows
+
+        def settle():
+            nonlocal in_flight
+            if in_flight is not None:
+                fut, in_flight = in_flight, None
+                emit(fut.result())
 
         def flush():
-            nonlocal batch, samples
-            rows = []
-            if stored is not None and stored.meta:
-                self._flush_stored(stored, rows)
-            if staged is not None and staged.meta:
-                self._flush_staged(staged, rows)
-            if batch:
-                self._flush(batch, rows)
-                batch = []
+            nonlocal cur, samples, in_flight
+            settle()                           # the other set of buffers is free again
+            in_flight = gpu.submit(run, sets[cur])
+            cur ^= 1
             samples = 0
-            rows.sort(key=lambda r: r[0])
-            emit(rows)
 
-        with pool:
+        try:
             while True:
                 while not exhausted and (ahead < self.batch_samples or not pending):
                     items, est = [], 0
@@ -553,44 +583,56 @@ class repeatDetector(object):
                 fut, est = pending.popleft()
                 ahead -= est
                 for item, raw in result(fut):
+                    b = sets[cur]
                     if raw is None:
                         logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
                         continue
                     if isinstance(raw, StoredRead):
-                        if stored is None:
-                            stored = _StoredStaging(self.batch_samples * 2 + (16 << 20))
                         for name in item[3]:
-                            if not stored.fits(len(raw.data)):
-                                flush()             # the I/O workers keep fetching the next batch meanwhile
-                                if not stored.fits(len(raw.data)):
-                                    stored.grow(len(raw.data))
-                            stored.add(item, name, raw)
+                            if b.stored is None:
+                                b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                            if not b.stored.fits(len(raw.data)):
+                                if b.stored.meta:
+                                    flush()         # the I/O workers keep fetching the next batch meanwhile
+                                    b = sets[cur]
+                                    if b.stored is None:
+                                        b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                                if not b.stored.fits(len(raw.data)):
+                                    b.stored.grow(len(raw.data))
+                            b.stored.add(item, name, raw)
                             samples += raw.n
                         if samples >= self.batch_samples:
                             flush()
                         continue
                     raw = np.asarray(raw)
                     stage_it = can_stage and raw.dtype == np.int16
-                    if stage_it and staged is None:
-                        staged = _Staging(self.batch_samples + (8 << 20))
                     if not stage_it and raw.base is not None:
                         raw = raw.copy()                # (a view into a worker's slot, which is about to be reused)
                     for name in item[3]:
                         if stage_it:
-                            if not staged.fits(len(raw)):
-                                flush()                 # the I/O workers keep fetching the next batch meanwhile
-                                if not staged.fits(len(raw)):
-                                    staged.grow(len(raw))
-                            staged.add(item, name, raw)
+                            if b.staged is None:
+                                b.staged = _Staging(self.batch_samples + (8 << 20))
+                            if not b.staged.fits(len(raw)):
+                                if b.staged.meta:
+                                    flush()
+                                    b = sets[cur]
+                                    if b.staged is None:
+                                        b.staged = _Staging(self.batch_samples + (8 << 20))
+                                if not b.staged.fits(len(raw)):
+                                    b.staged.grow(len(raw))
+                            b.staged.add(item, name, raw)
                         else:
-                            batch.append((item, raw, name))
+                            b.batch.append((item, raw, name))
                         samples += len(raw)
                     if samples >= self.batch_samples:
                         flush()
                 if hasattr(fut, 'release'):
                     fut.release()                       # the slot's signals have been copied out
-        if batch or (staged is not None and staged.meta) or (stored is not None and stored.meta):
-            flush()
+            if sets[cur].any():
+                flush()
+            settle()
+        finally:
+            gpu.shutdown(wait=True)
 
     def detect_records(self, work):
         """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""
@@ -710,7 +752,10 @@ def run_count(rd, lines, out, rank=0, world=1):
             ow.write_line([r for _, r in rows])
             logger.log('Main: {} rows after {:.2f} s'.format(n_rows, time.time() - t0), 'info')
 
-        rd.detect_stream(rd.plan_iter(lines), emit)
+        try:
+            rd.detect_stream(rd.plan_iter(lines), emit)
+        finally:
+            rd.close()
         ow.close()
         return n_rows
     ow = outputWriter(out) if rank == 0 else None

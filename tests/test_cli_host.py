@@ -138,7 +138,8 @@ def test_count_streams_input_and_appends_rows_batch_by_batch(tmp_path):
     # bounded prefetch: when line i is pulled, at most ~one batch (SEQ_LEN 100 * 9 = 900 estimated samples per read:
     # 12 reads) plus the pool's slack has been fetched beyond what was consumed
     assert all(nf <= i + 1 for i, _, nf in seen_at_yield)
-    assert max(i - w for i, w, _ in seen_at_yield) <= 30
+    # rows lag the input by at most the batch being fetched + the one being staged + the one on the GPU
+    assert max(i - w for i, w, _ in seen_at_yield) <= 42
 
 
 def test_failing_batch_is_retried_read_by_read(tmp_path):
