@@ -89,7 +89,7 @@ class sam_record(object):
 def decode_sam(sam_line):
     """scripts/STRique.py:656-671: QNAME / FLAG / RNAME / POS, reference length from CIGAR ops MDN=X,
     soft/hard clips from the first and last two CIGAR operations; empty record on any parse error."""
-    cols = sam_line.rstrip().split('\t')
+    cols = sam_line.split('\t', 10)          # (SEQ is field 10; QUAL and the tags stay unsplit in cols[10])
     sr = sam_record()
     if len(cols) >= 11:
         try:
@@ -207,7 +207,33 @@ def _worker_fetch_stored(read_ids, slot_name):
         else:
             recs.append(('s',))
             spill.append(raw)
+    if recs and all(r is not None and r[0] == 'c' for r in recs):
+        # the common case as arrays: the parent places the whole task with one copy and a few vector operations
+        counts = [len(r[3]) for r in recs]
+        return ('B', np.array([r[1] for r in recs], dtype=np.int64), np.array([r[2] for r in recs], dtype=np.int64),
+                np.repeat(np.arange(len(recs), dtype=np.int64), counts),
+                np.array([off0 for r in recs for off0, _ in r[3]], dtype=np.int64),
+                np.array([cs for r in recs for _, cs in r[3]], dtype=np.int64))
     return recs, spill, errs
+
+
+class StoredBlock(object):
+    """All reads of one worker task as stored chunks: samples and samples per chunk of every read; read, first sample
+    and stored bytes of every chunk; the stored bytes back to back (a view into the task's slot)."""
+    __slots__ = ('items', 'n', 'clen', 'chunk_read', 'off0', 'csize', 'data')
+
+    def __init__(self, items, n, clen, chunk_read, off0, csize, data):
+        self.items, self.n, self.clen, self.chunk_read, self.off0, self.csize, self.data = items, n, clen, chunk_read, off0, csize, data
+
+    def reads(self):
+        """the same, read by read"""
+        starts = np.concatenate(([0], np.cumsum(self.csize)))
+        first = np.searchsorted(self.chunk_read, np.arange(len(self.items) + 1))
+        for k, item in enumerate(self.items):
+            c0, c1 = int(first[k]), int(first[k + 1])
+            yield item, StoredRead(int(self.n[k]), int(self.clen[k]),
+                                   list(zip(self.off0[c0:c1].tolist(), self.csize[c0:c1].tolist())),
+                                   self.data[int(starts[c0]):int(starts[c1])])
 
 
 class _Staging(object):
@@ -249,7 +275,7 @@ class _StoredStaging(object):
         self.reset()
 
     def reset(self):
-        self.meta, self.offsets, self.pos, self.chunks, self.chunk_read = [], [0], 0, [], []
+        self.meta, self.offsets, self.pos, self._chunks, self._chunk_read = [], [0], 0, [], []
 
     def fits(self, nbytes):
         return self.pos + nbytes <= len(self.buf.array)
@@ -257,17 +283,39 @@ class _StoredStaging(object):
     def grow(self, nbytes):
         self.buf = self._lib.PinnedBuffer(nbytes + (nbytes >> 2), np.uint8)
 
-    def add(self, item, name, sr):
-        nb = len(sr.data)
-        self.buf.array[self.pos:self.pos + nb] = sr.data
-        base, src = self.offsets[-1], self.pos
-        for off0, cs in sr.chunks:
-            self.chunks.append((src, (base + off0) * 2, cs, min(sr.clen, sr.n - off0) * 2, sr.clen * 2, 0))
-            self.chunk_read.append(len(self.meta))
-            src += cs
+    def _place(self, n, clen, chunk_read, off0, csize, data):
+        """reads with n samples / clen samples per chunk; per chunk its read (0..), first sample, stored bytes"""
+        nb = len(data)
+        self.buf.array[self.pos:self.pos + nb] = data
+        base = self.offsets[-1] + np.cumsum(n) - n                        # first sample of every read in the batch
+        rec = np.zeros(len(csize), dtype=self._lib.INFLATE_CHUNK_DTYPE)
+        rec['src_off'] = self.pos + np.cumsum(csize) - csize
+        rec['dst_off'] = (base[chunk_read] + off0) * 2
+        rec['src_len'] = csize
+        rec['keep'] = np.minimum(clen[chunk_read], n[chunk_read] - off0) * 2
+        rec['full'] = clen[chunk_read] * 2
+        self._chunks.append(rec)
+        self._chunk_read.append(chunk_read + len(self.meta))
         self.pos += nb
-        self.offsets.append(base + sr.n)
+        self.offsets.extend((self.offsets[-1] + np.cumsum(n)).tolist())
+
+    def add(self, item, name, sr):
+        self._place(np.array([sr.n], dtype=np.int64), np.array([sr.clen], dtype=np.int64), np.zeros(len(sr.chunks), dtype=np.int64),
+                    np.array([c[0] for c in sr.chunks], dtype=np.int64), np.array([c[1] for c in sr.chunks], dtype=np.int64), sr.data)
         self.meta.append((item, name))
+
+    def add_block(self, blk):
+        """a whole worker task whose reads all have exactly one target"""
+        self._place(blk.n, blk.clen, blk.chunk_read, blk.off0, blk.csize, blk.data)
+        self.meta.extend((item, item[3][0]) for item in blk.items)
+
+    @property
+    def chunks(self):
+        return np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=self._lib.INFLATE_CHUNK_DTYPE)
+
+    @property
+    def chunk_read(self):
+        return np.concatenate(self._chunk_read) if self._chunk_read else np.zeros(0, dtype=np.int64)
 
 
 class repeatDetector(object):
@@ -378,12 +426,12 @@ class repeatDetector(object):
         """st: _StoredStaging -- compressed chunks to the device, inflated there"""
         from . import _lib
         targets = [(name, item[2]) for item, name in st.meta]
-        chunks = np.array(st.chunks, dtype=_lib.INFLATE_CHUNK_DTYPE)
+        chunks, chunk_read = st.chunks, st.chunk_read
         try:
             results, status = self.repeatCounter.detect_deflated(targets, st.buf.array, st.pos, chunks, st.offsets)
             results = list(results)
             for c in np.nonzero(status)[0]:
-                k = st.chunk_read[c]
+                k = int(chunk_read[c])
                 if results[k] is not None:
                     logger.log('Detector: damaged Signal chunk in read {} ({})'.format(
                         st.meta[k][0][1].QNAME, _lib.INFLATE_STATUS.get(int(status[c]), status[c])), 'warning')
@@ -414,7 +462,7 @@ class repeatDetector(object):
             logger.log('Detector: {}'.format(e), 'warning')
             return item, None
 
-    FETCH_CHUNK = 16                           # reads per task of a worker process
+    FETCH_CHUNK = 32                           # reads per task of a worker process
 
     def _get_pool(self):
         """--t worker processes reading fast5 (each loads the index itself; tasks of FETCH_CHUNK reads), or threads
@@ -444,7 +492,13 @@ class repeatDetector(object):
                 return fut
 
             def result(fut):
-                recs, spill, errs = fut.result()
+                res = fut.result()
+                fut.release = lambda: free.append(fut.shm)
+                if res[0] == 'B':
+                    nb = int(res[5].sum())
+                    return StoredBlock(fut.items, res[1], res[2], res[3], res[4], res[5],
+                                       np.frombuffer(fut.shm.buf, dtype=np.uint8)[:nb])
+                recs, spill, errs = res
                 for err in errs:
                     logger.log('Detector: {}'.format(err), 'warning')
                 out, pos, k = [], 0, 0
@@ -475,7 +529,6 @@ class repeatDetector(object):
                         else:
                             out.append((item, src[pos:pos + n]))      # a view: the caller copies it into its batch buffer
                             pos += n
-                fut.release = lambda: free.append(fut.shm)
                 return out
 
             def close_all():
@@ -582,7 +635,25 @@ class repeatDetector(object):
                     break
                 fut, est = pending.popleft()
                 ahead -= est
-                for item, raw in result(fut):
+                res = result(fut)
+                if isinstance(res, StoredBlock):
+                    if all(len(item[3]) == 1 for item in res.items):
+                        b = sets[cur]
+                        total = int(res.n.sum())
+                        if b.stored is not None and b.stored.meta and (samples + total > self.batch_samples or
+                                                                       not b.stored.fits(len(res.data))):
+                            flush()
+                            b = sets[cur]
+                        if b.stored is None:
+                            b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                        if not b.stored.fits(len(res.data)):
+                            b.stored.grow(len(res.data))
+                        b.stored.add_block(res)
+                        samples += total
+                        fut.release()
+                        continue
+                    res = res.reads()
+                for item, raw in res:
                     b = sets[cur]
                     if raw is None:
                         logger.log('Detector: No fast5 for ID {id}'.format(id=item[1].QNAME), 'warning')
