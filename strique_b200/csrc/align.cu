@@ -492,13 +492,21 @@ struct LinSweep2 {
             best = upd ? last : best;
             bestj = upd ? j : bestj;
         };
-        auto store_ck = [&](const int j, const bool before) {   // checkpoint column j: H = S[j-1] + g_h (before), S (after)
+        // checkpoint column j: H = S[j-1] + g_h (before), S (after).  One lane of the warp is at a checkpoint column in
+        // a step, so these stores cost the whole warp their issue slots: pairs (R, the lane offsets and the block
+        // offsets are even, the buffer holds 32 R + 1 rows) and no row predicates -- DP row 0 and the rows behind L
+        // are written but never read.
+        auto store_ck = [&](const int j, const bool before) {
             const size_t o = (size_t)(j / ALIGN_CKPT - 1) * 2 * ckpt_rows + lane * R;
+            float2 *dst = reinterpret_cast<float2 *>((before ? ckH : ckS) + o);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = lane * R + r;
-                if (i >= 1 && i <= L) {
-                    if (before) ckH[o + r] = Sv[r] + gh; else ckS[o + r] = Sv[r];
+            for (int m = 0; m < R / 2; ++m) {
+                if (before) {
+                    float h0, h1;
+                    f2_unpack(f2_add(f2_pack(Sv[2 * m], Sv[2 * m + 1]), gh2), h0, h1);
+                    dst[m] = make_float2(h0, h1);
+                } else {
+                    dst[m] = make_float2(Sv[2 * m], Sv[2 * m + 1]);
                 }
             }
         };
