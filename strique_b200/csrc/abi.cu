@@ -174,7 +174,8 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
            &d_tS = ctx->buf("al.tS"), &d_order = ctx->buf("al.order"), &d_ckoff = ctx->buf("al.ckoff"),
            &d_lut = ctx->buf("al.lut"), &d_ckpt = ctx->buf("al.ckpt"), &d_trace = ctx->buf("al.trace"),
            &d_rows = ctx->buf("al.rows"), &d_res = ctx->buf("al.res"), &d_queue = ctx->buf("al.queue"),
-           &d_fix = ctx->buf("al.fix"), &d_patch = ctx->buf("al.patch");
+           &d_fix = ctx->buf("al.fix"), &d_patch = ctx->buf("al.patch"), &d_ckstep = ctx->buf("al.ckstep"),
+           &d_pair_order = ctx->buf("al.pair_order"), &d_single_order = ctx->buf("al.single_order");
     // chunk tasks so LUT + checkpoints stay within a device-memory budget
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, ctx_mem_info(ctx, &free_b, &total_b));
@@ -212,6 +213,23 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
             ++t1;
         }
         const int n = t1 - t0;
+        // ---- pairs: two flanks over the same signal with the same kernel shape are scanned by one warp
+        // (LinSweepPair, linear gap costs only); their checkpoint areas are adjacent and become one interleaved area
+        std::vector<int32_t> ckstep(n, 1), pair_first(n, 0);
+        if (align_params_linear(params) && !getenv("STRIQUE_NO_PAIR_SCAN")) {
+            for (int t = 0; t + 1 < n;) {
+                if (task_signal[t0 + t] == task_signal[t0 + t + 1] && tS[t0 + t] == 6 && tS[t0 + t + 1] == 6 &&
+                    tK[t0 + t] == tK[t0 + t + 1]) {
+                    ckstep[t] = ckstep[t + 1] = 2;
+                    pair_first[t] = 1;
+                    ckoff[t + 1] = ckoff[t] + 1;
+                    t += 2;
+                } else {
+                    ++t;
+                }
+            }
+        }
+        TRY(d_ckstep.ensure(ctx, n * 4)); TRY(d_pair_order.ensure(ctx, n * 4)); TRY(d_single_order.ensure(ctx, n * 4));
         TRY(d_tsig.ensure(ctx, n * 4)); TRY(d_tflank.ensure(ctx, n * 4)); TRY(d_tpre.ensure(ctx, n * 4));
         TRY(d_tpost.ensure(ctx, n * 4)); TRY(d_tK.ensure(ctx, n * 4)); TRY(d_tS.ensure(ctx, n * 4));
         TRY(d_order.ensure(ctx, n * 4)); TRY(d_ckoff.ensure(ctx, n * 8));
@@ -229,6 +247,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         CUDA_TRY(ctx, up(d_tK, tK.data() + t0, n * 4));
         CUDA_TRY(ctx, up(d_tS, tS.data() + t0, n * 4));
         CUDA_TRY(ctx, up(d_ckoff, ckoff.data(), n * 8));
+        CUDA_TRY(ctx, up(d_ckstep, ckstep.data(), n * 4));
         CUDA_TRY(ctx, cudaMemsetAsync(d_res.p, 0, (size_t)n * sizeof(strique_align_result), ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(d_fix.p, 0, sizeof(unsigned long long), ctx->stream));
 
@@ -241,6 +260,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         b.task_pre = d_tpre.as<int32_t>(); b.task_post = d_tpost.as<int32_t>();
         b.lut = d_lut.as<float>(); b.lut_task_stride = lut_task_stride; b.lut_row = 32 * maxK;
         b.ckpt = d_ckpt.as<float>(); b.ckpt_off = d_ckoff.as<int64_t>(); b.ckpt_rows = ckpt_rows;
+        b.ckpt_step = d_ckstep.as<int32_t>();
         b.trace = d_trace.as<uint32_t>(); b.rows = d_rows.as<int32_t>(); b.rows_stride = rows_stride;
         b.res = d_res.as<strique_align_result>(); b.queue = d_queue.as<int>();
         b.lut_fix = d_fix.as<unsigned long long>(); b.lut_fix_cap = fix_cap;
@@ -291,14 +311,26 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         });
         CUDA_TRY(ctx, up(d_order, order.data(), n * 4));
         std::vector<AlignGroup> groups;
+        std::vector<int32_t> pair_order, single_order;      // per group: segments at the group's own offset
+        pair_order.reserve(n); single_order.reserve(n);
         for (int i = 0; i < n;) {
             int k = i;
             while (k < n && tK[t0 + order[k]] == tK[t0 + order[i]] && tS[t0 + order[k]] == tS[t0 + order[i]]) ++k;
             AlignGroup g;
             g.K = tK[t0 + order[i]]; g.S = tS[t0 + order[i]]; g.n_tasks = k - i; g.order = d_order.as<int32_t>() + i;
+            const size_t p0 = pair_order.size(), s0 = single_order.size();
+            for (int q = i; q < k; ++q) {
+                const int t = order[q];
+                if (pair_first[t]) pair_order.push_back(t);
+                else if (ckstep[t] == 1) single_order.push_back(t);
+            }
+            g.n_pairs = (int)(pair_order.size() - p0); g.pair_order = d_pair_order.as<int32_t>() + p0;
+            g.n_single = (int)(single_order.size() - s0); g.single_order = d_single_order.as<int32_t>() + s0;
             groups.push_back(g);
             i = k;
         }
+        if (!pair_order.empty()) CUDA_TRY(ctx, up(d_pair_order, pair_order.data(), pair_order.size() * 4));
+        if (!single_order.empty()) CUDA_TRY(ctx, up(d_single_order, single_order.data(), single_order.size() * 4));
         for (int t = 0; t < n; ++t) {
             const int f = task_flank[t0 + t];
             cells_total += len(t) * (int64_t)((in.flank_off_host[f + 1] - in.flank_off_host[f]) * in.samples);

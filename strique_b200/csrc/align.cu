@@ -569,6 +569,177 @@ struct LinSweep2 {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// LinSweepPair: the linear-gap scan of TWO tasks over the same signal (a read's prefix and suffix flank) by one
+// warp.  The two tasks share the column's code, the loop, the shuffle and the step bookkeeping, and ALL three adds
+// of the recurrence are packed across the two tasks (add.rn.f32x2 = two independent IEEE fp32 adds, so every value
+// is bit-identical to LinSweep's): 3 packed adds + 2 three-input maxima per row for two cells, 2.5 instructions per
+// cell instead of 3, and the per-column overhead is paid once for two tasks: 88 instructions per column and task
+// against 111 for LinSweep2.  Measured (C2, 8192 reads, 16 warps per SM): 87.1 ms against 94.3 ms; ncu: issue slots
+// 62 % busy, the packed adds (48 % of the instructions) wait on the FMA pipe (math-pipe throttle 19 % of the stall
+// samples) and on the column chain (fixed-latency wait 26 %).
+// Sv[2 r + t] is S of local row r of task t; checkpoints of the pair are stored interleaved (AlignBatch::ckpt_step).
+// ---------------------------------------------------------------------------------------------
+template <int K, int S>
+struct LinSweepPair {
+    static constexpr int R = K * S;
+
+    template <bool FIRST>
+    __device__ __forceinline__ static void column_scalar(float (&Sv)[2 * R], const float (&sc)[2 * K], const float (&diag)[2],
+                                                         float (&cS)[2], const float gh, const float gv) {
+        const float INF = STRIQUE_SEQAN_INF;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            float d = diag[t], c = cS[t];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float pS = Sv[2 * r + t];
+                const float inter = d + sc[2 * (r / S) + t];
+                d = pS;
+                const float h = (FIRST ? fmaxf(INF, pS) : pS) + gh;
+                c = fmax3(inter, h, c + gv);
+                Sv[2 * r + t] = c;
+            }
+            cS[t] = c;
+        }
+    }
+
+    __device__ __forceinline__ static unsigned long long column_pair(float (&Sv)[2 * R], const float (&sc)[2 * K],
+                                                                     unsigned long long diag2, unsigned long long cS2,
+                                                                     const unsigned long long gh2, const unsigned long long gv2) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long P = f2_pack(Sv[2 * r], Sv[2 * r + 1]);
+            float iA, iB, hA, hB, vA, vB;
+            f2_unpack(f2_add(diag2, f2_pack(sc[2 * (r / S)], sc[2 * (r / S) + 1])), iA, iB);
+            diag2 = P;
+            f2_unpack(f2_add(P, gh2), hA, hB);
+            f2_unpack(f2_add(cS2, gv2), vA, vB);
+            const float a = fmax3(iA, hA, vA), b = fmax3(iB, hB, vB);
+            Sv[2 * r] = a;
+            Sv[2 * r + 1] = b;
+            cS2 = f2_pack(a, b);
+        }
+        return cS2;
+    }
+
+    // kL[t]: level (inside its last lane) of the last DP row of task t; LASTFULL: both flanks end on the last row of
+    // their last lane (870 = 29 * 30), so the tracked cell is the lane's bottom register
+    template <bool LASTFULL>
+    __device__ __forceinline__ static void run(const uint16_t *__restrict__ codes, const int N, const float *__restrict__ lutA,
+                                               const float *__restrict__ lutB, const int lane, const int nl,
+                                               const strique_align_params &p, float (&Sv)[2 * R], unsigned long long diag_next2,
+                                               const int kLA, const int kLB, float (&best)[2], int (&bestj)[2],
+                                               float *__restrict__ ck, const int ckpt_rows) {
+        const float gh = p.gap_extension_h, gv = p.gap_extension_v;
+        const unsigned long long gh2 = f2_pack(gh, gh), gv2 = f2_pack(gv, gv);
+        const int row_len = 32 * K;
+        float lutc[2 * K], lutn[2 * K];
+        unsigned long long botS2 = 0ull;
+        const int last_step = N + nl - 1;
+        const float *lutA_lane = lutA + lane, *lutB_lane = lutB + lane;      // code row stored [k][lane]
+        auto fetch = [&](const int code, float (&dst)[2 * K]) {
+            const float *ra = lutA_lane + (size_t)code * row_len, *rb = lutB_lane + (size_t)code * row_len;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                dst[2 * k] = __ldg(ra + k * 32);
+                dst[2 * k + 1] = __ldg(rb + k * 32);
+            }
+        };
+        fetch(codes[clampi(-lane, 0, N - 1)], lutc);
+        int code_nx = codes[clampi(1 - lane, 0, N - 1)];
+        auto track_best = [&](const int j) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                float last = Sv[2 * (R - 1) + t];
+                if (!LASTFULL) {
+                    const int kL = t ? kLB : kLA;
+                    last = Sv[2 * (S - 1) + t];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) last = (kL == k) ? Sv[2 * ((k + 1) * S - 1) + t] : last;
+                }
+                // strict >: first maximum wins (dp_scout.h:175); only the last lane's (best, bestj) is read afterwards
+                const bool upd = last > best[t];
+                best[t] = upd ? last : best[t];
+                bestj[t] = upd ? j : bestj[t];
+            }
+        };
+        // checkpoint column j of both tasks, interleaved: [block][S | H][row i][task]; H = S[j-1] + g_h (before), S (after)
+        auto store_ck = [&](const int j, const bool before) {
+            float2 *dst = reinterpret_cast<float2 *>(ck + (size_t)(j / ALIGN_CKPT - 1) * 4 * ckpt_rows + (before ? 2 * ckpt_rows : 0)) +
+                          (lane * R + 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (before) {
+                    float h0, h1;
+                    f2_unpack(f2_add(f2_pack(Sv[2 * r], Sv[2 * r + 1]), gh2), h0, h1);
+                    dst[r] = make_float2(h0, h1);
+                } else {
+                    dst[r] = make_float2(Sv[2 * r], Sv[2 * r + 1]);
+                }
+            }
+        };
+        auto general = [&](const int st) {
+            const int j = st - lane;
+            fetch(code_nx, lutn);
+            const int code_nx2 = codes[clampi(j + 1, 0, N - 1)];
+            unsigned long long inS2 = __shfl_up_sync(0xffffffffu, botS2, 1);
+            if (lane == 0) inS2 = 0ull;              // DP row 0: free begin, S = 0
+            if (j > 0 && j <= N && lane < nl) {
+                const bool ck_col = (j & (ALIGN_CKPT - 1)) == 0;
+                if (ck_col) store_ck(j, true);
+                float diag[2], cS[2];
+                f2_unpack(diag_next2, diag[0], diag[1]);
+                f2_unpack(inS2, cS[0], cS[1]);
+                diag_next2 = inS2;
+                if (j == 1) column_scalar<true>(Sv, lutc, diag, cS, gh, gv);
+                else column_scalar<false>(Sv, lutc, diag, cS, gh, gv);
+                botS2 = f2_pack(cS[0], cS[1]);
+                if (ck_col) store_ck(j, false);
+                track_best(j);
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * K; ++k) lutc[k] = lutn[k];
+            code_nx = code_nx2;
+        };
+        const uint16_t *cptr = codes;
+        auto steady = [&](const int st, const float (&lc)[2 * K], float (&ln)[2 * K], auto with_ck) {
+            constexpr bool CK = decltype(with_ck)::value;
+            const int j = st - lane;
+            fetch(code_nx, ln);
+            const int code_nx2 = *cptr++;            // reads at most 2 codes past the signal (padded buffer)
+            unsigned long long inS2 = __shfl_up_sync(0xffffffffu, botS2, 1);
+            if (lane == 0) inS2 = 0ull;
+            const bool ck_col = CK && (j & (ALIGN_CKPT - 1)) == 0 && lane < nl;
+            if (CK && ck_col) store_ck(j, true);
+            const unsigned long long diag2 = diag_next2;
+            diag_next2 = inS2;
+            botS2 = column_pair(Sv, lc, diag2, inS2, gh2, gv2);
+            if (CK && ck_col) store_ck(j, false);
+            track_best(j);
+            code_nx = code_nx2;
+        };
+        int s = 1;
+        for (; s <= nl && s <= last_step; ++s) general(s);
+        cptr = codes + max(s - lane + 1, 0);
+        while (s + 1 <= N) {
+            const int m = s & (ALIGN_CKPT - 1);
+            if (m >= nl && m <= ALIGN_CKPT - 2) {
+                int pairs = min((ALIGN_CKPT - m) >> 1, (N - s + 1) >> 1);
+                for (; pairs > 0; --pairs, s += 2) {
+                    steady(s, lutc, lutn, std::false_type{});
+                    steady(s + 1, lutn, lutc, std::false_type{});
+                }
+            } else {
+                steady(s, lutc, lutn, std::true_type{});
+                steady(s + 1, lutn, lutc, std::true_type{});
+                s += 2;
+            }
+        }
+        for (; s <= last_step; ++s) general(s);
+    }
+};
+
 struct TaskGeom {
     int t, N, f, L, nl, lastlane, kL;
     const uint16_t *codes;
@@ -677,6 +848,56 @@ __global__ void __launch_bounds__(32, ALIGN_WARPS_PER_SM_PACKED) align_scan2_ker
     }
 }
 
+template <int K, int S>
+__global__ void __launch_bounds__(32, align_pair_warps(K)) align_scan_pair_kernel(AlignBatch b, AlignGroup grp) {
+    constexpr int R = K * S;
+    const int lane = threadIdx.x;
+    const float INF = STRIQUE_SEQAN_INF;
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(b.queue + 0, 1);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= grp.n_pairs) break;
+        const int tA = grp.pair_order[q];
+        const int sg = b.task_sig[tA];
+        const int N = (int)(b.sig_off[sg + 1] - b.sig_off[sg]);
+        float Sv[2 * R], best[2], diag0[2];
+        int bestj[2], lastlane[2], kL[2], nl = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int f = b.task_flank[tA + t];
+            const int L = (b.flank_off[f + 1] - b.flank_off[f]) * b.samples;
+            const float *col0 = b.col0 + (size_t)f * b.col0_stride;
+            nl = max(nl, (L + R - 1) / R);
+            lastlane[t] = (L - 1) / R;
+            kL[t] = ((L - 1) % R) / S;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = lane * R + r + 1;
+                Sv[2 * r + t] = i <= L ? col0[i] : 0.f;
+            }
+            diag0[t] = lane * R <= L ? col0[lane * R] : 0.f;
+            best[t] = INF;
+            bestj[t] = -1;
+            if (lane == lastlane[t] && col0[L] > INF) { best[t] = col0[L]; bestj[t] = 0; }
+        }
+        const float *lutA = b.lut + (size_t)tA * b.lut_task_stride, *lutB = lutA + b.lut_task_stride;
+        float *ck = b.ckpt + b.ckpt_off[tA];
+        if (kL[0] == K - 1 && kL[1] == K - 1)
+            LinSweepPair<K, S>::template run<true>(b.codes + b.sig_off[sg], N, lutA, lutB, lane, nl, b.p, Sv,
+                                                   f2_pack(diag0[0], diag0[1]), kL[0], kL[1], best, bestj, ck, b.ckpt_rows);
+        else
+            LinSweepPair<K, S>::template run<false>(b.codes + b.sig_off[sg], N, lutA, lutB, lane, nl, b.p, Sv,
+                                                    f2_pack(diag0[0], diag0[1]), kL[0], kL[1], best, bestj, ck, b.ckpt_rows);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (lane == lastlane[t]) {
+                b.res[tA + t].score = best[t];
+                b.res[tA + t].best_j = bestj[t];
+            }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pass 2: blockwise trace recomputation + SeqAn traceback (dp_traceback_impl.h:377-481,496-547).
 // ---------------------------------------------------------------------------------------------
@@ -742,15 +963,16 @@ __device__ __forceinline__ int trace_block(const AlignBatch &b, const TaskGeom &
         }
         diag0 = lane * R <= g.L ? g.col0[lane * R] : 0.f;
     } else {
-        const float *ckS = b.ckpt + b.ckpt_off[g.t] + (size_t)(blk - 1) * 2 * b.ckpt_rows;
-        const float *ckH = ckS + b.ckpt_rows;
+        const int step = b.ckpt_step[g.t];          // 2: interleaved with the other flank of the read (LinSweepPair)
+        const float *ckS = b.ckpt + b.ckpt_off[g.t] + (size_t)(blk - 1) * 2 * step * b.ckpt_rows;
+        const float *ckH = ckS + (size_t)step * b.ckpt_rows;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = lane * R + r + 1;
-            Sv[r] = i <= g.L ? ckS[i] : 0.f;
-            Hv[r] = i <= g.L ? ckH[i] : INF;
+            Sv[r] = i <= g.L ? ckS[(size_t)i * step] : 0.f;
+            Hv[r] = i <= g.L ? ckH[(size_t)i * step] : INF;
         }
-        diag0 = lane == 0 ? 0.f : (lane * R <= g.L ? ckS[lane * R] : 0.f);
+        diag0 = lane == 0 ? 0.f : (lane * R <= g.L ? ckS[(size_t)lane * R * step] : 0.f);
     }
     float capS = 0.f, capH = 0.f, capV = 0.f, dummy_best = 0.f;
     int dummy_j = 0;
@@ -875,6 +1097,22 @@ __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGrou
 template <int K, int S>
 int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
     const bool lin = align_params_linear(b.p);
+    if constexpr (S == 6) {
+        if (g.n_pairs > 0) {                         // (only set for linear gap costs, see align_run_device)
+            int grid = ctx->num_sms * align_pair_warps(K);
+            if (grid > g.n_pairs) grid = g.n_pairs;
+            align_scan_pair_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            if (g.n_single == 0) return STRIQUE_OK;
+            CUDA_TRY(ctx, cudaMemsetAsync(b.queue, 0, 4, ctx->stream));
+            AlignGroup rest = g;
+            rest.n_pairs = 0;
+            rest.n_tasks = g.n_single;
+            rest.order = g.single_order;
+            return launch_scan_t<K, S>(ctx, b, rest);
+        }
+    }
     if constexpr (S % 2 == 0) {
         if (lin && !getenv("STRIQUE_NO_PACKED_SCAN")) {
             int grid = ctx->num_sms * ALIGN_WARPS_PER_SM_PACKED;

@@ -28,6 +28,14 @@ namespace strique {
 constexpr int ALIGN_CKPT = STRIQUE_ALIGN_CKPT;   // columns between DP-column checkpoints (power of two)
 constexpr int ALIGN_WARPS_PER_SM = 8;    // resident single-warp CTAs per SM for the scan
 constexpr int ALIGN_WARPS_PER_SM_LINEAR = 16;   // ... for the linear-gap scan (half the registers)
+// ... for the two-flanks-per-warp scan (LinSweepPair): as many as the registers allow (12 K score registers + 4 K table
+// values + ~30 per thread).  Measured for K = 5 on 8192 C2 reads: 8 warps 101.0 ms, 10: 94.8, 12: 88.5, 14: 90.2,
+// 16: 87.1, 18 (96 registers, spills): 104.7.
+#ifdef ALIGN_PAIR_WARPS
+constexpr int align_pair_warps(int) { return ALIGN_PAIR_WARPS; }
+#else
+constexpr int align_pair_warps(int K) { return K <= 5 ? 16 : (K == 6 ? 12 : (K <= 8 ? 10 : 8)); }
+#endif
 #ifndef ALIGN_PACKED_WARPS
 #define ALIGN_PACKED_WARPS 16
 #endif
@@ -37,6 +45,10 @@ struct AlignGroup {        // tasks sharing one (K, S) kernel instantiation
     int K, S;
     int n_tasks;
     const int32_t *order;  // [n_tasks] task ids, longest signal first (device)
+    int n_pairs;           // scan only (linear gap costs): the first n_pairs entries of pair_order are tasks t such that
+    const int32_t *pair_order;   // t and t + 1 are two flanks over the SAME signal: one warp scans both (LinSweepPair);
+    int n_single;                // the remaining tasks follow in single_order
+    const int32_t *single_order;
 };
 
 // Device-side batch description (all pointers are device pointers).
@@ -57,6 +69,9 @@ struct AlignBatch {
     int lut_row;                  // floats per code row (32 * Kmax of the batch)
     float *ckpt;                  // checkpoints, see ckpt_off
     const int64_t *ckpt_off;      // [n_tasks] float offset of the task's checkpoint area
+    const int32_t *ckpt_step;     // [n_tasks] 1: the area is the task's own; 2: tasks t, t + 1 of a scanned pair share their
+                                  //   two areas, values interleaved (row i of the second task at [2 i + 1]; its offset is
+                                  //   the first task's + 1)
     int ckpt_rows;                // padded rows per checkpoint column (per S or H plane)
     uint32_t *trace;              // [n_warps_trace][ALIGN_CKPT][32][W] packed nibbles
     int32_t *rows;                // [n_tasks * rows_stride]
