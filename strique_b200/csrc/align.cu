@@ -726,6 +726,10 @@ struct LinSweepPair {
             const int m = s & (ALIGN_CKPT - 1);
             if (m >= nl && m <= ALIGN_CKPT - 2) {
                 int pairs = min((ALIGN_CKPT - m) >> 1, (N - s + 1) >> 1);
+#ifdef ALIGN_PAIR_UNROLL
+                constexpr int kUnroll = ALIGN_PAIR_UNROLL;
+#pragma unroll kUnroll
+#endif
                 for (; pairs > 0; --pairs, s += 2) {
                     steady(s, lutc, lutn, std::false_type{});
                     steady(s + 1, lutn, lutc, std::false_type{});
