@@ -18,4 +18,7 @@ for K in align_scan viterbi_profile_q align_trace; do
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$K" -c 1 -f -o "$OUT/${K}_$TAG" \
       python bench.py --steps 1 --warmup 0 --no-cpu-baseline > "$OUT/ncu_${K}_$TAG.log" 2>&1
 done
+echo "== ncu full: inflate"
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:inflate" -c 1 -f -o "$OUT/inflate_$TAG" \
+    python tools/inflate_probe.py 8192 6 > "$OUT/ncu_inflate_$TAG.log" 2>&1
 ls -la "$OUT"
