@@ -15,6 +15,7 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
+import re
 import sys
 import threading
 import time
@@ -312,27 +313,43 @@ def cli_e2e(args, n_reads, ctx=None):
         t0 = time.time()
         subprocess.run(cmd_empty, check=True, capture_output=True)
         t_start = time.time() - t0
-        t0 = time.time()
-        subprocess.run(cmd, check=True, capture_output=True)
-        wall = time.time() - t0
-        # the same with zlib on the worker processes (what the reference's h5py does)
-        t0 = time.time()
-        subprocess.run([os.path.join(tmp, 'out_host.tsv') if c == os.path.join(tmp, 'out.tsv') else c for c in cmd], check=True, capture_output=True,
-                       env=dict(os.environ, STRIQUE_HOST_INFLATE='1'))
-        wall_host = time.time() - t0
-        same = open(os.path.join(tmp, 'out_host.tsv')).read() == open(os.path.join(tmp, 'out.tsv')).read()
-        rows = open(os.path.join(tmp, 'out.tsv')).read().strip().split('\n')[1:]
+
+        def run(workers, host_inflate, out_name):
+            """one timed run -> wall clock of the process, and the rate between its first and its last GPU batch (rows
+            and times from the 'rows after' log lines: the process without start-up, first-use allocations and drain)"""
+            c = [os.path.join(tmp, out_name) if x == os.path.join(tmp, 'out.tsv') else x for x in cmd] + ['--log_level', 'info']
+            c[c.index('--t') + 1] = str(workers)
+            env = dict(os.environ, STRIQUE_HOST_INFLATE='1') if host_inflate else dict(os.environ)
+            env.pop('STRIQUE_HOST_INFLATE', None) if not host_inflate else None
+            t0 = time.time()
+            p = subprocess.run(c, check=True, capture_output=True, text=True, env=env)
+            wall = time.time() - t0
+            marks = [(int(m.group(1)), float(m.group(2))) for m in re.finditer(r'Main: (\d+) rows after ([0-9.]+) s', p.stderr)]
+            steady = (marks[-1][0] - marks[0][0]) / max(marks[-1][1] - marks[0][1], 1e-9) if len(marks) >= 3 else None
+            return {'value': n_reads / wall, 'wall_s': wall, 'value_after_startup': n_reads / max(wall - t_start, 1e-9),
+                    'between_first_and_last_batch': steady, 'batches': len(marks)}
+
+        t16 = min(cores, 32)
+        gpu16 = run(t16, False, 'out.tsv')
+        host16 = run(t16, True, 'out_host.tsv')
+        gpu4 = run(4, False, 'out_gpu4.tsv')
+        host4 = run(4, True, 'out_host4.tsv')
+        ref_rows = open(os.path.join(tmp, 'out.tsv')).read()
+        same = all(open(os.path.join(tmp, f)).read() == ref_rows for f in ('out_host.tsv', 'out_gpu4.tsv', 'out_host4.tsv'))
+        rows = ref_rows.strip().split('\n')[1:]
         truth = {('synth-%08d' % k): r[3] for k, r in enumerate(reads)}
         exact = sum(1 for r in rows if int(r.split('\t')[3]) == truth[r.split('\t')[0]])
         fast5_mb = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.endswith('.fast5')) / 1e6
-        return {'value': n_reads / wall, 'unit': 'reads/s', 'reads': n_reads, 'wall_s': wall, 'startup_s': t_start,
-                'value_after_startup': n_reads / max(wall - t_start, 1e-9), 'io_workers': min(cores, 32),
-                'rows': len(rows), 'count_exact': exact, 'fast5_mb': fast5_mb, 'dataset_build_s': t_make,
-                'inflate': 'GPU (strique_inflate_batch)', 'inflate_kernel': inflate,
-                'host_inflate': {'value': n_reads / wall_host, 'wall_s': wall_host,
-                                 'value_after_startup': n_reads / max(wall_host - t_start, 1e-9), 'same_rows': same},
-                'what': 'scripts/STRique.py count <index> <model> <panel_config> --algn <sam> --t <workers> --out <tsv> on '
-                        'multi-read fast5 files (deflate), wall clock of the process'}
+        out = dict(gpu16)
+        out.update({'unit': 'reads/s', 'reads': n_reads, 'startup_s': t_start, 'io_workers': t16, 'rows': len(rows),
+                    'count_exact': exact, 'fast5_mb': fast5_mb, 'dataset_build_s': t_make,
+                    'inflate': 'GPU (strique_inflate_batch)', 'inflate_kernel': inflate,
+                    'host_inflate': host16, 'io_workers_4': {'gpu_inflate': gpu4, 'host_inflate': host4},
+                    'same_rows_in_all_runs': same,
+                    'what': 'scripts/STRique.py count <index> <model> <panel_config> --algn <sam> --t <workers> --out <tsv> on '
+                            'multi-read fast5 files (deflate), wall clock of the process; host_inflate = the same with zlib '
+                            'on the worker processes (STRIQUE_HOST_INFLATE=1), like the reference\'s h5py'})
+        return out
     except Exception as e:  # noqa: BLE001 - the hot-path numbers above must survive a failure here
         return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
     finally:

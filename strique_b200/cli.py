@@ -268,9 +268,10 @@ class _StoredStaging(object):
     """Reads of one GPU batch as fast5 stores them: the zlib streams of their Signal chunks back to back in ONE
     page-locked byte buffer + one strique_inflate_chunk record per chunk.  The samples only ever exist on the device."""
 
-    def __init__(self, capacity_bytes):
+    def __init__(self, capacity_bytes, small=False):
         from . import _lib
         self._lib = _lib
+        self.small = small                       # the quarter-size buffer of a run's first batch (see detect_stream)
         self.buf = _lib.PinnedBuffer(capacity_bytes, np.uint8)
         self.reset()
 
@@ -589,8 +590,37 @@ class repeatDetector(object):
 
         sets = [Buffers(), Buffers()]
         cur = 0
+        clock = {'io': 0.0, 'stage': 0.0, 'gpu_wait': 0.0, 'alloc': 0.0}     # where this thread's time goes (log level info)
         gpu = ThreadPoolExecutor(1)
         in_flight = None                       # future of the batch on the GPU
+        # Page-locking memory costs ~0.5 ms per MB, 0.3 s for one batch's buffer.  The first batch of a run is a
+        # quarter batch in a quarter-size buffer -- the GPU starts early -- while the two full-size buffers are
+        # allocated on a helper thread.
+        full_cap = self.batch_samples * 3 // 2 + (16 << 20)
+        alloc = ThreadPoolExecutor(1)
+        spare = deque()
+
+        def stored_for(b):
+            t0 = time.time()
+            try:
+                return stored_for_(b)
+            finally:
+                clock['alloc'] += time.time() - t0
+
+        def stored_for_(b):
+            if b.stored is None or (b.stored.small and not b.stored.meta):
+                if b.stored is None and not spare and not any(x.stored is not None for x in sets):
+                    spare.append(alloc.submit(_StoredStaging, full_cap))
+                    spare.append(alloc.submit(_StoredStaging, full_cap))
+                    b.stored = _StoredStaging(full_cap // 4, small=True)
+                elif spare:
+                    b.stored = spare.popleft().result()
+                elif b.stored is None:
+                    b.stored = _StoredStaging(full_cap)
+            return b.stored
+
+        def limit(b):
+            return self.batch_samples // 4 if (b.stored is not None and b.stored.small) else self.batch_samples
 
         def run(b):
             rows = []
@@ -608,7 +638,10 @@ class repeatDetector(object):
             nonlocal in_flight
             if in_flight is not None:
                 fut, in_flight = in_flight, None
-                emit(fut.result())
+                t0 = time.time()
+                rows = fut.result()
+                clock['gpu_wait'] += time.time() - t0
+                emit(rows)
 
         def flush():
             nonlocal cur, samples, in_flight
@@ -635,17 +668,19 @@ class repeatDetector(object):
                     break
                 fut, est = pending.popleft()
                 ahead -= est
+                t0 = time.time()
                 res = result(fut)
+                t1 = time.time()
+                clock['io'] += t1 - t0
                 if isinstance(res, StoredBlock):
                     if all(len(item[3]) == 1 for item in res.items):
                         b = sets[cur]
                         total = int(res.n.sum())
-                        if b.stored is not None and b.stored.meta and (samples + total > self.batch_samples or
+                        if b.stored is not None and b.stored.meta and (samples + total > limit(b) or
                                                                        not b.stored.fits(len(res.data))):
                             flush()
                             b = sets[cur]
-                        if b.stored is None:
-                            b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                        stored_for(b)
                         if not b.stored.fits(len(res.data)):
                             b.stored.grow(len(res.data))
                         b.stored.add_block(res)
@@ -660,19 +695,17 @@ class repeatDetector(object):
                         continue
                     if isinstance(raw, StoredRead):
                         for name in item[3]:
-                            if b.stored is None:
-                                b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                            stored_for(b)
                             if not b.stored.fits(len(raw.data)):
                                 if b.stored.meta:
                                     flush()         # the I/O workers keep fetching the next batch meanwhile
                                     b = sets[cur]
-                                    if b.stored is None:
-                                        b.stored = _StoredStaging(self.batch_samples * 3 // 2 + (16 << 20))
+                                    stored_for(b)
                                 if not b.stored.fits(len(raw.data)):
                                     b.stored.grow(len(raw.data))
                             b.stored.add(item, name, raw)
                             samples += raw.n
-                        if samples >= self.batch_samples:
+                        if samples >= limit(b):
                             flush()
                         continue
                     raw = np.asarray(raw)
@@ -702,8 +735,11 @@ class repeatDetector(object):
             if sets[cur].any():
                 flush()
             settle()
+            logger.log('Detector: waited {io:.2f} s for the I/O workers, {gpu_wait:.2f} s for the GPU, {alloc:.2f} s for '
+                       'staging buffers'.format(**clock), 'info')
         finally:
             gpu.shutdown(wait=True)
+            alloc.shutdown(wait=True)
 
     def detect_records(self, work):
         """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""
