@@ -157,7 +157,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         tS[t] = S;
         maxRows = std::max(maxRows, 32 * K * S);
         maxK = std::max(maxK, K);
-        maxW = std::max(maxW, (K * S + 7) / 8);
+        maxW = std::max(maxW, 4 * ((K * S + 31) / 32));       // trace words per lane and column: four flag planes
     }
     const int ckpt_rows = (int)align_up(maxRows + 1, 32);
     const int64_t lut_task_stride = (int64_t)in.n_code_values * 32 * maxK;

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
 template <int K, int S, bool TRACE>
 struct Sweep {
     static constexpr int R = K * S;
-    static constexpr int W = (R + 7) / 8;
+    static constexpr int WP = (R + 31) / 32;     // trace words per flag plane
+    static constexpr int W = 4 * WP;             // trace words per lane and column: planes gap | maxh | hopen | vopen
 
     __device__ __forceinline__ static void run(
         const uint16_t *__restrict__ codes, const int N, const float *__restrict__ lut, const int j0, const int j1,
@@ -167,8 +168,12 @@ struct Sweep {
                         const bool gap = inter < g;
                         cS = gap ? g : inter;
                         Hv[r] = h;
-                        const uint32_t nib = (gap ? (maxh ? 2u : 1u) : 0u) | (hopen ? 4u : 0u) | (vopen ? 8u : 0u);
-                        tw[r / 8] |= nib << (4 * (r % 8));
+                        // one bit per flag and row, in four planes: a predicated OR per flag instead of assembling and
+                        // shifting a nibble (the trace pass is bound by the integer pipe: 27 -> 22 instructions per cell)
+                        if (gap) tw[r / 32] |= 1u << (r % 32);
+                        if (maxh) tw[WP + r / 32] |= 1u << (r % 32);
+                        if (hopen) tw[2 * WP + r / 32] |= 1u << (r % 32);
+                        if (vopen) tw[3 * WP + r / 32] |= 1u << (r % 32);
                         if ((r + 1) % S == 0 && j == capture_j && lane == lastlane && kL == r / S) {
                             capS = cS; capH = h; capV = cV;
                         }
@@ -908,14 +913,14 @@ __global__ void __launch_bounds__(32, align_pair_warps(K)) align_scan_pair_kerne
 template <int K, int S>
 __device__ __forceinline__ unsigned trace_at(const uint32_t *trace, int j0, int j, int i) {
     constexpr int R = K * S;
-    constexpr int W = (R + 7) / 8;
+    constexpr int WP = (R + 31) / 32, W = 4 * WP;
     if (i <= 0 || j <= 0) return 0u;   // DP row 0 carries no trace; column 0 is never followed
     const int li = (i - 1) / R, r = (i - 1) % R;
-    const uint32_t w = trace[((size_t)li * ALIGN_CKPT + (j - j0 - 1)) * W + r / 8];   // L1-cached (see the writer)
-    const unsigned nib = (w >> (4 * (r % 8))) & 15u;
-    const unsigned src = nib & 3u;
-    return (src == 0 ? T_DIAG : (src == 1 ? T_MAXV : T_MAXH)) | ((nib & 4u) ? T_HOPEN : T_HOR) |
-           ((nib & 8u) ? T_VOPEN : T_VER);
+    const uint32_t *w = trace + ((size_t)li * ALIGN_CKPT + (j - j0 - 1)) * W + r / 32;   // L1-cached (see the writer)
+    const int bit = r % 32;
+    const bool gap = (w[0] >> bit) & 1u, maxh = (w[WP] >> bit) & 1u, hopen = (w[2 * WP] >> bit) & 1u,
+               vopen = (w[3 * WP] >> bit) & 1u;
+    return (!gap ? T_DIAG : (maxh ? T_MAXH : T_MAXV)) | (hopen ? T_HOPEN : T_HOR) | (vopen ? T_VOPEN : T_VER);
 }
 
 __device__ __forceinline__ int nearest_signal_index(const int32_t *rows, int L, int N, int q) {
@@ -1042,7 +1047,7 @@ __device__ __forceinline__ int trace_block(const AlignBatch &b, const TaskGeom &
 template <int K, int S>
 __global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGroup grp) {
     constexpr int R = K * S;
-    constexpr int W = (R + 7) / 8;
+    constexpr int W = 4 * ((R + 31) / 32);       // trace words per lane and column (Sweep::W of the widest variant)
     constexpr int K2 = (K + 1) / 2, K4 = (K + 3) / 4, K8 = (K + 7) / 8;   // fewer levels per lane for blocks entered at a small row
     const int lane = threadIdx.x;
     uint32_t *trace = b.trace + (size_t)blockIdx.x * ALIGN_CKPT * 32 * W;

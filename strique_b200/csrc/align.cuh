@@ -73,7 +73,7 @@ struct AlignBatch {
                                   //   two areas, values interleaved (row i of the second task at [2 i + 1]; its offset is
                                   //   the first task's + 1)
     int ckpt_rows;                // padded rows per checkpoint column (per S or H plane)
-    uint32_t *trace;              // [n_warps_trace][ALIGN_CKPT][32][W] packed nibbles
+    uint32_t *trace;              // [n_warps_trace][32][ALIGN_CKPT][W] flag bits: planes gap | maxh | hopen | vopen
     int32_t *rows;                // [n_tasks * rows_stride]
     int64_t rows_stride;
     strique_align_result *res;    // [n_tasks]
