@@ -6,9 +6,12 @@
 // delete chain as a max-plus scan, one back-pointer word per lane per column), different arithmetic
 // (profile_q.h): tagged int32 fixed-point scores, so that ONE VIADDMNMX per in-edge relaxes the edge and carries
 // the winner's name -- no compare / select chains, no 64-bit shuffles, half the registers.  The decoded path is
-// re-scored in float64 during the traceback (log p = exact score of the returned path); sequences the fixed-point
-// pass cannot vouch for (samples outside the fast emission range, unreachable END, forward value and re-score
-// disagreeing beyond the quantisation bound) get status 3 and are decoded by the float64 kernel instead.
+// re-scored in float64 during the traceback (log p = exact score of the returned path).  The floor clamp of the
+// renormalisation only ever raises values, so every forward value is an upper bound of the true fixed-point score;
+// the traceback re-adds the quantised weights along the decoded path in int64, and equality with the forward value
+// (plus: no clamped emission, no absent edge on the path) PROVES the path optimal for the quantised model.  A
+// sequence the pass cannot vouch for (that proof fails, a sample outside the fast emission range, END unreachable)
+// is decoded again in float64 by the same warp before it takes its next sequence (decode_float64; reserved = 1).
 #include <math.h>
 
 #include <algorithm>
