@@ -6,12 +6,13 @@
 
 #include "../../strique_b200/csrc/inflate_core.h"
 
-// misalign: the stream is placed at this byte offset (0..3) of an aligned buffer, as chunks are inside a batch
+// misalign: the stream is placed at this byte offset (0..15) of a 16-byte aligned buffer, as chunks are inside a batch
 extern "C" int strique_test_inflate(const uint8_t *src, long long n, int misalign, uint8_t *out, unsigned keep, uint8_t *spill,
                                     unsigned full, unsigned *produced) {
     using namespace strique::inf;
-    std::vector<uint32_t> words((size_t)(n + misalign) / 4 + 4, 0xA5A5A5A5u);     // garbage around the stream
+    std::vector<uint32_t> words((size_t)(n + misalign) / 4 + 16, 0xA5A5A5A5u);    // garbage around the stream
     uint8_t *base = reinterpret_cast<uint8_t *>(words.data());
+    base += (16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15;
     memcpy(base + misalign, src, (size_t)n);
     std::vector<uint16_t> lit(1 << LIT_BITS), dist(1 << DIST_BITS);
     Scratch s;

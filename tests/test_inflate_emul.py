@@ -74,7 +74,7 @@ def test_every_block_type_and_strategy_matches_zlib(emul):
     for pname, data in payloads():
         for sname, stream in streams(data):
             assert zlib.decompress(stream) == data
-            for misalign in (0, 1, 3):
+            for misalign in (0, 1, 3, 4, 7, 12, 15):
                 st, got = run(emul, stream, len(data), misalign=misalign)
                 assert st == 0, (pname, sname, misalign, st)
                 assert got == data, (pname, sname, misalign)
