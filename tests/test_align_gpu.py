@@ -181,3 +181,48 @@ def test_flank_beyond_the_kernels_is_refused_when_the_target_is_defined(ctx, mod
     rd = counter.repeatCounter(model_file, context=ctx)
     with pytest.raises(ValueError, match='does not fit the alignment kernels'):
         rd.add_target('long', 'GGCCCC', 'ACGT' * 100, C9_SUFFIX)
+
+
+def test_two_flanks_per_warp_scan_equals_single_task_scan_and_oracle(ctx, monkeypatch):
+    """csrc/align.cu LinSweepPair (both flanks of a signal scanned by one warp, checkpoints interleaved) against the
+    single-task kernels (STRIQUE_NO_PAIR_SCAN) and the oracle: signals shorter than the lane count, around the
+    checkpoint spacing, flanks of different length inside one kernel shape (different last lane / last level), a flank
+    that fills its last lane exactly, and an odd task left over without a partner."""
+    c = rp.CAligner()
+    ps = ac.PARAM_SETS[0]
+    _set(c, ps)
+    rng = np.random.default_rng(41)
+    levels = [np.round(rng.uniform(60, 120, n), 2).astype(np.float32) for n in (145, 129, 160, 97)]   # K = 5, 5, 5(6?), 4
+    flank_off = np.cumsum([0] + [len(l) for l in levels])
+    sig_lens = [1, 7, 29, 31, 200, 511, 512, 513, 1023, 1025, 2500, 6000]
+    sigs, codes, vals, off = [], [], [], [0]
+    for n in sig_lens:
+        lev = levels[0]
+        a = np.round(rng.uniform(60, 120, n))
+        if n > 1200:                                         # plant both flanks so that the paths are long
+            p = np.round(np.repeat(levels[0], rng.integers(6, 9, len(levels[0]))))[:n // 3]
+            a[10:10 + len(p)] = p
+        cc, vv = sa.encode_signal(a)
+        v = np.zeros(256, np.float32); v[:len(vv)] = vv
+        sigs.append(a); codes.append(cc.astype(np.uint8)); vals.append(v); off.append(off[-1] + n)
+    tasks = []
+    for si in range(len(sigs)):
+        tasks += [(si, 0), (si, 1)]                          # a pair (same kernel shape, different L)
+        if si % 3 == 0:
+            tasks += [(si, 2)]                               # left over: no partner of its shape
+        if si % 4 == 1:
+            tasks += [(si, 3), (si, 3)]                      # another shape, the same flank twice
+    args = (ps, np.concatenate(codes), off, np.stack(vals), np.concatenate(levels), flank_off, 6,
+            [t[0] for t in tasks], [t[1] for t in tasks], [0] * len(tasks), [0] * len(tasks))
+    monkeypatch.delenv('STRIQUE_NO_PAIR_SCAN', raising=False)
+    paired = ctx.align_batch(*args)
+    monkeypatch.setenv('STRIQUE_NO_PAIR_SCAN', '1')
+    single = ctx.align_batch(*args)
+    monkeypatch.delenv('STRIQUE_NO_PAIR_SCAN', raising=False)
+    for name in ('score', 'best_j', 'begin0', 'end0', 'begin_trim', 'end_trim'):
+        assert np.array_equal(paired[name], single[name]), name
+    for k, (si, fi) in enumerate(tasks):
+        s0, a0, b0 = c.align_overlap(sigs[si], np.repeat(levels[fi], 6))
+        assert np.float32(paired['score'][k]) == np.float32(s0), (sig_lens[si], fi)
+        want = ac.detect_range_indices(a0, b0, 0, 0)
+        assert (paired['begin0'][k], paired['end0'][k], paired['begin_trim'][k], paired['end_trim'][k]) == want, (sig_lens[si], fi)
