@@ -868,28 +868,31 @@ def run_count(rd, lines, out, rank=0, world=1):
     ow = outputWriter(out) if rank == 0 else None
     plan = rd.plan_iter(lines) if rank == 0 else None
     chunk_samples = rd.batch_samples * world
-    while True:
-        work = None
-        if rank == 0:
-            work, est = [], 0
-            for item in plan:
-                work.append(item)
-                est += max(item[1].SEQ_LEN, 1) * rd.SAMPLES_PER_BASE * len(item[3])
-                if est >= chunk_samples:
-                    break
-            if not work:
-                work = None
-        work = sharding.broadcast_object(work)
-        if work is None:
-            break
-        # cost of a read ~ its length (2 flank alignments over the whole signal dominate)
-        shards = sharding.lpt_partition([w[1].SEQ_LEN * len(w[3]) for w in work], world)
-        rows = rd.detect_records([work[i] for i in shards[rank]])
-        rows = sharding.gather_rows(rows)
-        if rank == 0:
-            n_rows += len(rows)
-            ow.write_line([r for _, r in rows])
-            logger.log('Main: {} rows after {:.2f} s'.format(n_rows, time.time() - t0), 'info')
+    try:
+        while True:
+            work = None
+            if rank == 0:
+                work, est = [], 0
+                for item in plan:
+                    work.append(item)
+                    est += max(item[1].SEQ_LEN, 1) * rd.SAMPLES_PER_BASE * len(item[3])
+                    if est >= chunk_samples:
+                        break
+                if not work:
+                    work = None
+            work = sharding.broadcast_object(work)
+            if work is None:
+                break
+            # cost of a read ~ its length (2 flank alignments over the whole signal dominate)
+            shards = sharding.lpt_partition([w[1].SEQ_LEN * len(w[3]) for w in work], world)
+            rows = rd.detect_records([work[i] for i in shards[rank]])
+            rows = sharding.gather_rows(rows)
+            if rank == 0:
+                n_rows += len(rows)
+                ow.write_line([r for _, r in rows])
+                logger.log('Main: {} rows after {:.2f} s'.format(n_rows, time.time() - t0), 'info')
+    finally:
+        rd.close()                               # (the I/O workers live across the chunks)
     if rank == 0:
         ow.close()
     logger.log('Main: rank {} done in {:.2f} s'.format(rank, time.time() - t0), 'info')
