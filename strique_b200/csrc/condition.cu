@@ -6,6 +6,11 @@ namespace strique {
 namespace {
 
 constexpr int CT = 512;     // threads per CTA
+// resident CTAs per SM: the kernel waits on L2 (12 dependent passes over a read), so threads in flight matter more than
+// registers per thread -- 2 CTAs (63 registers) 10.1 ms per 8192 reads, 3 (40 registers) 7.2 ms, 4 (32, spills) 8.1 ms
+#ifndef COND_MIN_CTAS
+#define COND_MIN_CTAS 3
+#endif
 constexpr int MAXR = 6;     // ranks resolved per radix-select round
 
 template <typename T> struct KeyTraits;
@@ -255,7 +260,7 @@ __device__ __forceinline__ int hist_at(const unsigned *h, int rank) {   // value
 }
 
 template <typename T>
-__global__ void __launch_bounds__(CT) condition_kernel(const T *__restrict__ raw_all, const int64_t *__restrict__ off,
+__global__ void __launch_bounds__(CT, COND_MIN_CTAS) condition_kernel(const T *__restrict__ raw_all, const int64_t *__restrict__ off,
                                                        int n_reads, CondModel model, int want_raw, T *__restrict__ flt_all,
                                                        uint16_t *__restrict__ codes_all, uint8_t *__restrict__ tmpA_all,
                                                        uint8_t *__restrict__ tmpB_all, float *__restrict__ vals_all,
