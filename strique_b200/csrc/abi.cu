@@ -180,7 +180,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, ctx_mem_info(ctx, &free_b, &total_b));
     const size_t budget = std::max<size_t>((size_t)1 << 30, (size_t)(free_b * 0.6));
-    const int trace_warps = ctx->num_sms * (getenv("STRIQUE_TRACE_WARPS") ? atoi(getenv("STRIQUE_TRACE_WARPS")) : 12);   // single-warp CTAs per SM (168 registers for K = 5)
+    const int trace_warps = ctx->num_sms * (getenv("STRIQUE_TRACE_WARPS") ? atoi(getenv("STRIQUE_TRACE_WARPS")) : ALIGN_TRACE_WARPS_MAX);   // single-warp CTAs (see align_trace_warps)
     const int fix_cap = 1 << 16;
 
     TRY(d_col0.ensure(ctx, col0.size() * sizeof(float)));

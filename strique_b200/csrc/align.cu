@@ -1045,7 +1045,7 @@ __device__ __forceinline__ int trace_block(const AlignBatch &b, const TaskGeom &
 }
 
 template <int K, int S>
-__global__ void __launch_bounds__(32) align_trace_kernel(AlignBatch b, AlignGroup grp) {
+__global__ void __launch_bounds__(32, align_trace_warps(K * S)) align_trace_kernel(AlignBatch b, AlignGroup grp) {
     constexpr int R = K * S;
     constexpr int W = 4 * ((R + 31) / 32);       // trace words per lane and column (Sweep::W of the widest variant)
     constexpr int K2 = (K + 1) / 2, K4 = (K + 3) / 4, K8 = (K + 7) / 8;   // fewer levels per lane for blocks entered at a small row
@@ -1145,7 +1145,7 @@ int launch_scan_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g) {
 
 template <int K, int S>
 int launch_trace_t(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &g, int n_warps) {
-    int grid = n_warps;
+    int grid = std::min(n_warps, ctx->num_sms * align_trace_warps(K * S));     // (n_warps sized the trace buffer)
     if (grid > g.n_tasks) grid = g.n_tasks;
     align_trace_kernel<K, S><<<grid, 32, 0, ctx->stream>>>(b, g);
     ctx->launches++;

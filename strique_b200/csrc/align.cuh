@@ -28,6 +28,15 @@ namespace strique {
 constexpr int ALIGN_CKPT = STRIQUE_ALIGN_CKPT;   // columns between DP-column checkpoints (power of two)
 constexpr int ALIGN_WARPS_PER_SM = 8;    // resident single-warp CTAs per SM for the scan
 constexpr int ALIGN_WARPS_PER_SM_LINEAR = 16;   // ... for the linear-gap scan (half the registers)
+// ... for the trace pass (rows = K * S score and H registers each): the recomputation is issue bound with plenty of
+// fixed-latency waits, so resident warps beat registers -- K = 5, 8192 C2 reads: 12 warps per SM (168 registers)
+// 18.5 ms, 14 (128 registers, 80 B of spills) 16.4, 16: 15.7, 20 (96 registers): 18.3.
+#ifdef ALIGN_TRACE_WARPS
+constexpr int align_trace_warps(int) { return ALIGN_TRACE_WARPS; }
+#else
+constexpr int align_trace_warps(int rows) { return rows <= 32 ? 16 : (rows <= 42 ? 12 : 8); }
+#endif
+constexpr int ALIGN_TRACE_WARPS_MAX = 16;
 // ... for the two-flanks-per-warp scan (LinSweepPair): as many as the registers allow (12 K score registers + 4 K table
 // values + ~30 per thread).  Measured for K = 5 on 8192 C2 reads: 8 warps 101.0 ms, 10: 94.8, 12: 88.5, 14: 90.2,
 // 16: 87.1, 18 (96 registers, spills): 104.7.
