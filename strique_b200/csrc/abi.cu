@@ -268,39 +268,7 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TABLE);
         TRY(align_launch_build_lut(ctx, b, d_tK.as<int32_t>(), d_tS.as<int32_t>(), n));
         stage_mark(ctx, 2 * STRIQUE_STAGE_ALIGN_TABLE + 1);
-        // ---- patch table entries too close to an fp32 rounding midpoint with libm's pow -------
-        CUDA_TRY(ctx, cudaMemcpyAsync(fix_host.data(), d_fix.p, (1 + 2 * fix_head) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const unsigned long long nfix = fix_host[0];
-        if (nfix > (unsigned long long)fix_cap) FAIL(ctx, STRIQUE_EUNSUPPORTED, "too many borderline score-table entries");
-        if (nfix > fix_head)
-            CUDA_TRY(ctx, cudaMemcpy(fix_host.data() + 1 + 2 * fix_head, (char *)d_fix.p + (1 + 2 * fix_head) * 8, (nfix - fix_head) * 16, cudaMemcpyDeviceToHost));
-        if (nfix) {
-            patch_host.resize(2 * nfix);
-            for (unsigned long long k = 0; k < nfix; ++k) {
-                const int t = (int)(fix_host[1 + 2 * k] >> 40);
-                const int64_t e = (int64_t)(fix_host[1 + 2 * k] & ((1ull << 40) - 1));
-                const int Kt = tK[t0 + t], row_len = 32 * Kt;
-                const int c = (int)(e / row_len), u = (int)(e % row_len);
-                float h, v;
-                const uint32_t hb = (uint32_t)(fix_host[2 + 2 * k] >> 32), vb = (uint32_t)fix_host[2 + 2 * k];
-                memcpy(&h, &hb, 4);
-                memcpy(&v, &vb, 4);
-                const float d = h > v ? h - v : v - h;
-                volatile float fx = (float)pow((double)d, 1.2);
-                volatile float sc = params.dist_offset - fx;
-                const float out = sc > params.dist_min ? sc : params.dist_min;
-                uint32_t ob;
-                memcpy(&ob, &out, 4);
-                const int64_t pos = (int64_t)c * row_len + (u % Kt) * 32 + u / Kt;       // stored [u % K][u / K] inside the code row
-                patch_host[2 * k] = (unsigned long long)((int64_t)t * lut_task_stride + pos);
-                patch_host[2 * k + 1] = ob;
-            }
-            // (pageable source: the copy returns once the host buffer has been staged, so patch_host may be reused)
-            CUDA_TRY(ctx, cudaMemcpyAsync(d_patch.p, patch_host.data(), nfix * 16, cudaMemcpyHostToDevice, ctx->stream));
-            TRY(align_launch_patch_lut(ctx, b.lut, d_patch.as<unsigned long long>(), (int)nfix));
-        }
-        // ---- groups by kernel instantiation, longest signal first -----------------------------
+        // ---- groups by kernel instantiation, longest signal first (host work while the table kernel runs) ----
         std::vector<int32_t> order(n);
         std::iota(order.begin(), order.end(), 0);
         auto len = [&](int t) { return in.sig_off_host[task_signal[t0 + t] + 1] - in.sig_off_host[task_signal[t0 + t]]; };
@@ -334,6 +302,38 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         for (int t = 0; t < n; ++t) {
             const int f = task_flank[t0 + t];
             cells_total += len(t) * (int64_t)((in.flank_off_host[f + 1] - in.flank_off_host[f]) * in.samples);
+        }
+        // ---- patch table entries too close to an fp32 rounding midpoint with libm's pow -------
+        CUDA_TRY(ctx, cudaMemcpyAsync(fix_host.data(), d_fix.p, (1 + 2 * fix_head) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const unsigned long long nfix = fix_host[0];
+        if (nfix > (unsigned long long)fix_cap) FAIL(ctx, STRIQUE_EUNSUPPORTED, "too many borderline score-table entries");
+        if (nfix > fix_head)
+            CUDA_TRY(ctx, cudaMemcpy(fix_host.data() + 1 + 2 * fix_head, (char *)d_fix.p + (1 + 2 * fix_head) * 8, (nfix - fix_head) * 16, cudaMemcpyDeviceToHost));
+        if (nfix) {
+            patch_host.resize(2 * nfix);
+            for (unsigned long long k = 0; k < nfix; ++k) {
+                const int t = (int)(fix_host[1 + 2 * k] >> 40);
+                const int64_t e = (int64_t)(fix_host[1 + 2 * k] & ((1ull << 40) - 1));
+                const int Kt = tK[t0 + t], row_len = 32 * Kt;
+                const int c = (int)(e / row_len), u = (int)(e % row_len);
+                float h, v;
+                const uint32_t hb = (uint32_t)(fix_host[2 + 2 * k] >> 32), vb = (uint32_t)fix_host[2 + 2 * k];
+                memcpy(&h, &hb, 4);
+                memcpy(&v, &vb, 4);
+                const float d = h > v ? h - v : v - h;
+                volatile float fx = (float)pow((double)d, 1.2);
+                volatile float sc = params.dist_offset - fx;
+                const float out = sc > params.dist_min ? sc : params.dist_min;
+                uint32_t ob;
+                memcpy(&ob, &out, 4);
+                const int64_t pos = (int64_t)c * row_len + (u % Kt) * 32 + u / Kt;       // stored [u % K][u / K] inside the code row
+                patch_host[2 * k] = (unsigned long long)((int64_t)t * lut_task_stride + pos);
+                patch_host[2 * k + 1] = ob;
+            }
+            // (pageable source: the copy returns once the host buffer has been staged, so patch_host may be reused)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_patch.p, patch_host.data(), nfix * 16, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(align_launch_patch_lut(ctx, b.lut, d_patch.as<unsigned long long>(), (int)nfix));
         }
         // ---- pass 1: scan (timed) -------------------------------------------------------------
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
