@@ -71,3 +71,23 @@ def test_bundled_read_documented_integers(model_file):
     out = r.detect('c9orf72', raw, '-')
     assert (int(out[4]), int(out[5])) == (1633, 40758)
     assert abs(out[0] - 735) <= 2
+
+
+def test_pore_model_constants_and_template_signal(model_file, mod_model_file):
+    """SURVEY §8 a1 / a2 (scripts/STRique.py:114-127, 182-195): the four scalars of both shipped models as verified
+    against the reference's own arithmetic, 1185 k-mers that differ between the two tables, and the noise-free
+    template signal = k-mer means repeated `samples` times ((len - 5) * samples values)."""
+    import numpy as np
+    from strique_b200.pore_model import pore_model
+    pm, pmm = pore_model(model_file), pore_model(mod_model_file)
+    for got, want in zip((pm.model_median, pm.model_MAD, pm.model_min, pm.model_max), (91.1925, 10.6584, 49.5413, 133.1231)):
+        assert abs(got - want) < 5e-5
+    for got, want in zip((pmm.model_median, pmm.model_MAD, pmm.model_min, pmm.model_max), (91.2150, 10.7271, 47.3526, 131.3527)):
+        assert abs(got - want) < 5e-5
+    seq = 'ACGTTGCA' * 20
+    sig = np.asarray(pm.generate_signal(seq, samples=6))
+    assert len(sig) == (len(seq) - 5) * 6
+    means = np.asarray(pm.kmer_means(seq))
+    assert np.array_equal(sig, np.repeat(means, 6))
+    ref = rp.PoreModel(model_file)
+    assert np.array_equal(sig, np.asarray(ref.generate_signal(seq, samples=6)))
