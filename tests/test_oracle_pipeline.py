@@ -75,7 +75,7 @@ def test_bundled_read_documented_integers(model_file):
 
 def test_pore_model_constants_and_template_signal(model_file, mod_model_file):
     """SURVEY §8 a1 / a2 (scripts/STRique.py:114-127, 182-195): the four scalars of both shipped models as verified
-    against the reference's own arithmetic, 1185 k-mers that differ between the two tables, and the noise-free
+    against the reference's own arithmetic, and the noise-free
     template signal = k-mer means repeated `samples` times ((len - 5) * samples values)."""
     import numpy as np
     from strique_b200.pore_model import pore_model
