@@ -4,6 +4,7 @@ There is no CPU fallback: importing works anywhere (so host logic can be tested 
 but creating a `Context` without the compiled library or without a B200 raises `StriqueError`.
 """
 import ctypes
+import threading
 import os
 
 import numpy as np
@@ -394,7 +395,11 @@ class PinnedBuffer(object):
 _default_ctx = {}
 
 
+_default_ctx_lock = threading.Lock()
+
+
 def default_context(device=0):
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
+    with _default_ctx_lock:                      # (the CLI creates it on a helper thread while its I/O workers start)
+        if device not in _default_ctx:
+            _default_ctx[device] = Context(device)
+        return _default_ctx[device]

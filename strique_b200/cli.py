@@ -23,6 +23,7 @@ import os
 import re
 import signal
 import sys
+import threading
 import time
 from collections import defaultdict, deque
 from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor
@@ -331,7 +332,17 @@ class repeatDetector(object):
         self.f5 = fast5.fast5Index(fast5_index_file)
         self.io_threads = max(int(io_threads), 1)
         self._io = None
-        self._get_pool()                       # worker processes start (and load the index) while the CUDA context comes up
+        if counter is None:
+            # the CUDA context (~0.5 s) comes up on a helper thread while the worker processes are started
+            from . import _lib
+
+            def warm():
+                try:
+                    _lib.default_context(device)
+                except Exception:  # noqa: BLE001 - reported by the first real use
+                    pass
+            threading.Thread(target=warm, daemon=True).start()
+        self._get_pool()                       # worker processes start (and load the index) meanwhile
         self.repeatCounter = counter or repeatCounter(model_file, mod_model_file=mod_model_file,
                                                       align_config=align_config, HMM_config=HMM_config, device=device)
         self.repeatLoci = defaultdict(list)
