@@ -564,7 +564,8 @@ class repeatDetector(object):
         return self._io[1:]
 
     def close(self):
-        """stop the I/O workers and release their shared-memory slots"""
+        """stop the I/O workers and release their shared-memory slots (and the staging buffers kept between calls)"""
+        self._kept_stored = []
         io, self._io = getattr(self, '_io', None), None
         if io is not None:
             io[0]()
@@ -610,6 +611,12 @@ class repeatDetector(object):
         full_cap = self.batch_samples * 3 // 2 + (16 << 20)
         alloc = ThreadPoolExecutor(1)
         spare = deque()
+        # buffers of an earlier call of this detector (the multi-rank path calls once per chunk): no ramp-up then
+        kept = [st for st in getattr(self, '_kept_stored', []) if len(st.buf.array) >= full_cap]
+        self._kept_stored = []
+        for k, st in enumerate(kept[:2]):
+            st.reset()
+            sets[k].stored = st
 
         def stored_for(b):
             t0 = time.time()
@@ -751,6 +758,14 @@ class repeatDetector(object):
         finally:
             gpu.shutdown(wait=True)
             alloc.shutdown(wait=True)
+            # keep the full-size page-locked buffers for the next call
+            keep = [b.stored for b in sets if b.stored is not None and not b.stored.small]
+            for fut in spare:
+                try:
+                    keep.append(fut.result())
+                except Exception:  # noqa: BLE001
+                    pass
+            self._kept_stored = keep[:2]
 
     def detect_records(self, work):
         """work: output of plan() (possibly one rank's share). -> list of (input index, row tuple)."""
