@@ -202,7 +202,11 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         int t1 = t0;
         std::vector<int64_t> ckoff;
         int64_t ck_floats = 0;
-        while (t1 < n_tasks && t1 - t0 < 60000) {
+        // at most 60000 tasks per chunk (the table kernel's grid), the remaining tasks in equal (even: pairs) shares --
+        // a short last chunk would run the kernels at a fraction of their occupancy
+        const int remaining = n_tasks - t0, n_chunks_left = (remaining + 59999) / 60000;
+        const int chunk_cap = (((remaining + n_chunks_left - 1) / n_chunks_left) + 1) & ~1;
+        while (t1 < n_tasks && t1 - t0 < chunk_cap) {
             const int64_t N = in.sig_off_host[task_signal[t1] + 1] - in.sig_off_host[task_signal[t1]];
             const int64_t nck = N / ALIGN_CKPT;
             const size_t need = (size_t)lut_task_stride * 4 + (size_t)nck * 2 * ckpt_rows * 4 + (size_t)rows_stride * 4;
