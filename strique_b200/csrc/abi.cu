@@ -202,9 +202,11 @@ int align_run_device(strique_ctx *ctx, const strique_align_params &params, const
         int t1 = t0;
         std::vector<int64_t> ckoff;
         int64_t ck_floats = 0;
-        // at most 60000 tasks per chunk (the table kernel's grid), the remaining tasks in equal (even: pairs) shares --
-        // a short last chunk would run the kernels at a fraction of their occupancy
-        const int remaining = n_tasks - t0, n_chunks_left = (remaining + 59999) / 60000;
+        // at most 60000 tasks per chunk, the remaining tasks in equal (even: pairs) shares -- a short last chunk would
+        // run the kernels at a fraction of their occupancy; the memory budget below may still cut a chunk short.
+        // (Nothing forces the 60000: one chunk of 65536 tasks measured 407 ms of scan against 378 ms for two of 32768.)
+        const int max_chunk = 60000;
+        const int remaining = n_tasks - t0, n_chunks_left = (remaining + max_chunk - 1) / max_chunk;
         const int chunk_cap = (((remaining + n_chunks_left - 1) / n_chunks_left) + 1) & ~1;
         while (t1 < n_tasks && t1 - t0 < chunk_cap) {
             const int64_t N = in.sig_off_host[task_signal[t1] + 1] - in.sig_off_host[task_signal[t1]];

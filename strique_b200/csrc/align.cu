@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
     // pairs and skip pow altogether.  The tile goes through shared memory so that the table rows (code-major)
     // are still written coalesced.
     extern __shared__ float tile[];                  // [tile_codes][row_len + 1]
-    const int t = blockIdx.y;
+    const int t = blockIdx.x;             // (tasks along x: no 65535 limit)
     if (t >= n_tasks) return;
     const int K = task_K[t], S = task_S[t];
     const int f = b.task_flank[t], sg = b.task_sig[t];
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) align_build_lut_kernel(AlignBatch b, cons
     const float *lev = b.flank_levels + b.flank_off[f];
     float *lut = b.lut + (size_t)t * b.lut_task_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int c0 = blockIdx.x * tile_codes; c0 < b.n_code_values; c0 += gridDim.x * tile_codes) {
+    for (int c0 = blockIdx.y * tile_codes; c0 < b.n_code_values; c0 += gridDim.y * tile_codes) {
         const int c = c0 + lane;
         const bool mine = lane < tile_codes && c < b.n_code_values;
         const float h = mine ? vals[c] : 0.f;
@@ -1200,8 +1200,7 @@ int align_launch_trace(strique_ctx *ctx, const AlignBatch &b, const AlignGroup &
 int align_launch_build_lut(strique_ctx *ctx, const AlignBatch &b, const int32_t *task_K, const int32_t *task_S,
                            int n_tasks) {
     if (n_tasks == 0) return STRIQUE_OK;
-    if (n_tasks > 65535) FAIL(ctx, STRIQUE_EINVAL, "alignment chunk larger than 65535 tasks");
-    dim3 grid(8, n_tasks);
+    dim3 grid(n_tasks, 8);
     float far = INFINITY;
     const double span = (double)b.p.dist_offset - (double)b.p.dist_min;
     if (span > 0.0 && span < 1e30) far = (float)(pow(span * (1.0 + 1e-5), 1.0 / 1.2) * (1.0 + 1e-6));
